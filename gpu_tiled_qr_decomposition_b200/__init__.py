@@ -1,0 +1,200 @@
+"""gpu_tiled_qr_decomposition_b200 -- ctypes binding of libqrb200.so.
+
+The product is the C-ABI shared library (include/qrb200.h, include/gpucalc_compat.h) built
+from csrc/ for sm_100a; this module only loads it for the Python test/bench harness.  There
+is NO CPU fallback: if the library is missing, or no CUDA device is usable, calls raise.
+"""
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libqrb200.so")
+
+TILE = 32
+QRS, SAPP, QRD, DAPP = 0, 1, 2, 3
+TASK_AVAIL, TASK_NONE, TASK_DONE = 0, 1, 2
+
+# every symbol include/qrb200.h and include/gpucalc_compat.h declare
+EXPORTS = (
+    "b200qr_version", "b200qr_strerror", "b200qr_last_cuda_error", "b200qr_device_sm_count",
+    "b200qr_measure_fp32_peak",
+    "b200qr_plan_create", "b200qr_plan_destroy", "b200qr_plan_grid", "b200qr_plan_tile_tasks",
+    "b200qr_plan_macro_tasks", "b200qr_factor_device", "b200qr_plan_tau_device",
+    "b200qr_tau_to_reference", "b200qr_factor_host", "b200qr_plan_read_trace", "b200qr_tile_task",
+    "b200qr_sched_init", "b200qr_sched_next", "b200qr_sched_done", "b200qr_sched_free",
+    "b200qr_sched_progress", "b200qr_sched_ready_count", "b200qr_sched_dep_count",
+    "b200qr_sched_predecessors", "b200qr_sched_device_order",
+    "cudaQRTask", "cudaQRFull", "testDAPP", "doCUDADAPP",
+)
+
+
+class QRError(RuntimeError):
+    pass
+
+
+class Task(C.Structure):
+    _fields_ = [("type", C.c_int), ("l", C.c_int), ("m", C.c_int), ("k", C.c_int)]
+
+
+class Opts(C.Structure):
+    _fields_ = [("grid_ctas", C.c_int), ("trace", C.c_int), ("reserved", C.c_int * 6)]
+
+
+def build(force=False):
+    """Compile libqrb200.so in-tree with nvcc for sm_100a (no GPU needed)."""
+    srcs = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))]
+    srcs.append(os.path.join(os.path.dirname(HERE), "include", "qrb200.h"))
+    stale = force or not os.path.exists(LIB_PATH) or any(
+        os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if stale:
+        r = subprocess.run(["make", "-C", HERE, "libqrb200.so"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise QRError("building libqrb200.so failed:\n" + r.stdout + r.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """The loaded library (raises QRError if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise QRError("libqrb200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                          "there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp, ip, fp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)
+        L.b200qr_strerror.restype = C.c_char_p
+        L.b200qr_strerror.argtypes = [C.c_int]
+        L.b200qr_measure_fp32_peak.argtypes = [C.POINTER(C.c_double), C.c_int]
+        L.b200qr_plan_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(Opts)]
+        L.b200qr_plan_destroy.argtypes = [vp]
+        L.b200qr_plan_grid.argtypes = [vp]
+        L.b200qr_plan_tile_tasks.argtypes = [vp]
+        L.b200qr_plan_tile_tasks.restype = C.c_long
+        L.b200qr_plan_macro_tasks.argtypes = [vp]
+        L.b200qr_plan_macro_tasks.restype = C.c_long
+        L.b200qr_factor_device.argtypes = [vp, vp, C.c_int, vp]
+        L.b200qr_plan_tau_device.argtypes = [vp]
+        L.b200qr_plan_tau_device.restype = vp
+        L.b200qr_tau_to_reference.argtypes = [vp, vp, C.c_int, vp]
+        L.b200qr_factor_host.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, fp]
+        L.b200qr_plan_read_trace.argtypes = [vp, vp, C.c_long]
+        L.b200qr_tile_task.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int]
+        L.b200qr_sched_init.argtypes = [C.c_int, C.c_int]
+        L.b200qr_sched_init.restype = vp
+        L.b200qr_sched_next.argtypes = [vp, C.POINTER(Task)]
+        L.b200qr_sched_done.argtypes = [vp, C.POINTER(Task)]
+        L.b200qr_sched_free.argtypes = [vp]
+        L.b200qr_sched_progress.argtypes = [vp, C.c_int, C.c_int]
+        L.b200qr_sched_ready_count.argtypes = [vp]
+        L.b200qr_sched_dep_count.argtypes = [C.c_int, C.c_int]
+        L.b200qr_sched_predecessors.argtypes = [C.POINTER(Task), C.POINTER(Task)]
+        L.b200qr_sched_device_order.argtypes = [C.c_int, C.c_int, vp, C.c_long]
+        L.b200qr_sched_device_order.restype = C.c_long
+        L.cudaQRTask.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.cudaQRTask.restype = None
+        L.cudaQRFull.argtypes = [vp, C.c_int, C.c_int]
+        L.cudaQRFull.restype = None
+        L.testDAPP.argtypes = [vp, C.c_int, C.c_int]
+        L.testDAPP.restype = None
+        L.doCUDADAPP.argtypes = [vp]
+        L.doCUDADAPP.restype = None
+        _lib = L
+    return _lib
+
+
+def check(rc, what="libqrb200"):
+    if rc != 0:
+        L = lib()
+        raise QRError("%s failed: %s (cuda error %d)" % (what, L.b200qr_strerror(rc).decode(),
+                                                        L.b200qr_last_cuda_error()))
+
+
+class Plan:
+    """Workspace + schedule for one (m, n) shape (b200qr_plan_*)."""
+
+    def __init__(self, m, n, grid_ctas=0, trace=False):
+        self.m, self.n = m, n
+        self._h = C.c_void_p()
+        o = Opts()
+        o.grid_ctas, o.trace = int(grid_ctas), int(bool(trace))
+        check(lib().b200qr_plan_create(C.byref(self._h), m, n, C.byref(o)), "b200qr_plan_create")
+
+    @property
+    def grid(self):
+        return lib().b200qr_plan_grid(self._h)
+
+    @property
+    def tile_tasks(self):
+        return lib().b200qr_plan_tile_tasks(self._h)
+
+    @property
+    def macro_tasks(self):
+        return lib().b200qr_plan_macro_tasks(self._h)
+
+    def factor(self, dptr, ldm, stream=0):
+        """Factor the device matrix at address `dptr` in place (asynchronous on `stream`)."""
+        check(lib().b200qr_factor_device(self._h, C.c_void_p(dptr), ldm, C.c_void_p(stream)),
+              "b200qr_factor_device")
+
+    def tau_to_reference(self, dptr, ldtau, stream=0):
+        check(lib().b200qr_tau_to_reference(self._h, C.c_void_p(dptr), ldtau, C.c_void_p(stream)),
+              "b200qr_tau_to_reference")
+
+    def read_trace(self):
+        import numpy as np
+        n = self.tile_tasks
+        out = np.zeros((n, 6), dtype=np.int32)
+        check(lib().b200qr_plan_read_trace(self._h, out.ctypes.data_as(C.c_void_p), n), "b200qr_plan_read_trace")
+        return out
+
+    def close(self):
+        if self._h:
+            lib().b200qr_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def factor_host(a, m, n, ldm=None, want_tau=False):
+    """b200qr_factor_host on a NumPy (n, ldm) float32 array (column-major m x n), in place.
+    Returns (kernel_ms, tau-or-None)."""
+    import numpy as np
+    ldm = ldm or m
+    assert a.dtype == np.float32 and a.flags.c_contiguous and a.shape == (n, ldm)
+    tau = np.zeros_like(a) if want_tau else None
+    ms = C.c_float(0)
+    check(lib().b200qr_factor_host(a.ctypes.data_as(C.c_void_p), m, n, ldm,
+                                   tau.ctypes.data_as(C.c_void_p) if want_tau else None, C.byref(ms)),
+          "b200qr_factor_host")
+    return ms.value, tau
+
+
+def sched_trace(M, N):
+    """Serial trace of the host scheduler mirror with the reference's pick rule."""
+    import numpy as np
+    L = lib()
+    s = L.b200qr_sched_init(M, N)
+    t = Task()
+    out = []
+    while L.b200qr_sched_next(s, C.byref(t)) == TASK_AVAIL:
+        out.append((t.type, t.l, t.m, t.k))
+        L.b200qr_sched_done(s, C.byref(t))
+    L.b200qr_sched_free(s)
+    return np.array(out, dtype=np.int32).reshape(-1, 4)
+
+
+def device_order(M, N):
+    import numpy as np
+    cap = sum((M - k) * (N - k) for k in range(min(M, N)))
+    out = np.zeros((cap, 4), dtype=np.int32)
+    n = lib().b200qr_sched_device_order(M, N, out.ctypes.data_as(C.c_void_p), cap)
+    assert n == cap, (n, cap)
+    return out

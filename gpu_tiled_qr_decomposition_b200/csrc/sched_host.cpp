@@ -1,0 +1,165 @@
+// sched_host.cpp -- host mirror of the tile-DAG scheduler in progress-word form.
+//
+// The reference keeps one Task slot per tile whose (k, taskStatus) pair encodes how far
+// the tile has got (src/gridscheduler.c:51-64 genericdone).  Here that pair is collapsed
+// into one integer per tile, prog[l][m] = number of completed steps, which is exactly the
+// word the persistent CUDA kernel spins on.  Task (l,m,k) of type
+//   QRS  (l==k, m==k)  needs prog[k][k]   == k
+//   SAPP (l==k, m> k)  needs prog[k][m]   == k  and prog[k][k]   >= k+1
+//   QRD  (l> k, m==k)  needs prog[l][k]   == k  and prog[l-1][k] >= k+1
+//   DAPP (l> k, m> k)  needs prog[l][m]   == k  and prog[l][k]   >= k+1 and prog[l-1][m] >= k+1
+// (gridscheduler.c:112-174 candoQRS/SAPP/QRD/DAPP).  Driven by one serial worker with the
+// reference's pick rule (gridscheduler.c:259-300) it reproduces the reference's task
+// sequence; tests/test_sched.py checks that against the golden traces.
+#include "../../include/qrb200.h"
+
+#include <cstdlib>
+#include <vector>
+
+namespace {
+enum : unsigned char { S_IDLE = 0, S_READY = 1, S_DOING = 2 };
+
+inline int task_type(int l, int m, int k)
+{
+    if (l == k) return m == k ? B200QR_QRS : B200QR_SAPP;
+    return m == k ? B200QR_QRD : B200QR_DAPP;
+}
+}  // namespace
+
+struct b200qr_sched_s {
+    int M, N;
+    std::vector<int> prog;              // column-major like the reference's tgrid: [m*M + l]
+    std::vector<unsigned char> state;
+    int ready;
+
+    int &P(int l, int m) { return prog[(size_t)m * M + l]; }
+    unsigned char &S(int l, int m) { return state[(size_t)m * M + l]; }
+    bool inside(int l, int m) const { return l >= 0 && m >= 0 && l < M && m < N; }
+
+    // all inputs of the tile's next task are final?
+    bool runnable(int l, int m)
+    {
+        if (!inside(l, m)) return false;
+        int k = P(l, m);
+        if (k > (l < m ? l : m)) return false;          // tile has no task left
+        if (l > k && P(l - 1, m) < k + 1) return false;  // tile above finished step k
+        if (m > k && P(l, k) < k + 1) return false;      // panel tile of this row finished step k
+        return true;
+    }
+    void promote(int l, int m)
+    {
+        if (inside(l, m) && S(l, m) == S_IDLE && runnable(l, m)) { S(l, m) = S_READY; ++ready; }
+    }
+};
+
+extern "C" {
+
+b200qr_sched_t b200qr_sched_init(int M, int N)
+{
+    if (M <= 0 || N <= 0) return nullptr;
+    b200qr_sched_s *s = new b200qr_sched_s;
+    s->M = M; s->N = N; s->ready = 0;
+    s->prog.assign((size_t)M * N, 0);
+    s->state.assign((size_t)M * N, S_IDLE);
+    s->promote(0, 0);                                    // gridscheduler.c:320 seeds QRS(0,0)
+    return s;
+}
+
+void b200qr_sched_free(b200qr_sched_t s) { delete s; }
+
+int b200qr_sched_next(b200qr_sched_t s, b200qr_task *out)
+{
+    bool busy = false;
+    for (int l = s->M - 1; l >= 0; --l)
+        for (int m = s->N - 1; m >= 0; --m) {
+            unsigned char st = s->S(l, m);
+            if (st == S_READY) {
+                s->S(l, m) = S_DOING; --s->ready;
+                int k = s->P(l, m);
+                out->type = task_type(l, m, k); out->l = l; out->m = m; out->k = k;
+                return B200QR_TASK_AVAIL;
+            }
+            if (st == S_DOING) busy = true;
+        }
+    return busy ? B200QR_TASK_NONE : B200QR_TASK_DONE;
+}
+
+void b200qr_sched_done(b200qr_sched_t s, const b200qr_task *t)
+{
+    int l = t->l, m = t->m;
+    int k = s->P(l, m);
+    int type = task_type(l, m, k);
+    s->S(l, m) = S_IDLE;
+    s->P(l, m) = k + 1;
+    // Who can this completion unblock?  Same neighbourhoods the reference probes
+    // (gridscheduler.c:188-253), expressed on progress words.
+    if (type == B200QR_QRS || type == B200QR_QRD)
+        for (int j = k + 1; j < s->N; ++j) s->promote(l, j);   // the panel row to the right
+    if (type == B200QR_DAPP) s->promote(l, m);                 // same tile, next step
+    s->promote(l + 1, m);                                      // the tile below
+}
+
+int b200qr_sched_progress(b200qr_sched_t s, int l, int m) { return s->inside(l, m) ? s->P(l, m) : -1; }
+int b200qr_sched_ready_count(b200qr_sched_t s) { return s->ready; }
+
+int b200qr_sched_dep_count(int type, int k)
+{
+    int prev = k > 0 ? 1 : 0;            // DAPP(l,m,k-1) on the same tile
+    switch (type) {
+    case B200QR_QRS:  return prev;
+    case B200QR_SAPP: return 1 + prev;   // QRS(k,k,k)
+    case B200QR_QRD:  return 1 + prev;   // task above in the panel column
+    case B200QR_DAPP: return 2 + prev;   // QRD(l,k,k) and the task above in column m
+    }
+    return -1;
+}
+
+int b200qr_sched_predecessors(const b200qr_task *t, b200qr_task pred[3])
+{
+    int n = 0, l = t->l, m = t->m, k = t->k;
+    if (k > 0) pred[n++] = b200qr_task{B200QR_DAPP, l, m, k - 1};
+    if (m > k) pred[n++] = b200qr_task{task_type(l, k, k), l, k, k};        // QRS (l==k) or QRD
+    if (l > k) pred[n++] = b200qr_task{task_type(l - 1, m, k), l - 1, m, k};
+    return n;
+}
+
+// Ticket order of the persistent kernel (see DESIGN.md "scheduler"): macro tasks
+//   P(k)   = QRS(k,k) followed by the QRD chain down tile column k,
+//   S(k,g) = for each tile column j of column group g: SAPP(k,j) then the DAPP chain,
+// issued as P(0), then for every step k: S(k,g0), P(k+1), S(k,g0+1), S(k,g0+2), ...
+// Must stay in lock-step with decode_ticket() in qr_persistent.cu (tests compare both).
+long b200qr_sched_device_order(int M, int N, int *out4, long cap)
+{
+    const int G = 4;                                     // tile columns per sweep task
+    int K = M < N ? M : N;
+    long n = 0;
+    auto emit = [&](int type, int l, int m, int k) {
+        if (n < cap) { out4[4 * n] = type; out4[4 * n + 1] = l; out4[4 * n + 2] = m; out4[4 * n + 3] = k; }
+        ++n;
+    };
+    auto panel = [&](int k) {
+        emit(B200QR_QRS, k, k, k);
+        for (int i = k + 1; i < M; ++i) emit(B200QR_QRD, i, k, k);
+    };
+    auto sweep = [&](int k, int g) {
+        int j0 = g * G > k + 1 ? g * G : k + 1;
+        int j1 = (g + 1) * G < N ? (g + 1) * G : N;
+        // the 4 warps of a sweep CTA advance row by row together
+        for (int j = j0; j < j1; ++j) emit(B200QR_SAPP, k, j, k);
+        for (int i = k + 1; i < M; ++i)
+            for (int j = j0; j < j1; ++j) emit(B200QR_DAPP, i, j, k);
+    };
+    panel(0);
+    int GB = (N + G - 1) / G;
+    for (int k = 0; k < K; ++k) {
+        bool has_cols = k + 1 < N;
+        int g0 = (k + 1) / G;
+        if (has_cols) sweep(k, g0);
+        if (k + 1 < K) panel(k + 1);
+        if (has_cols)
+            for (int g = g0 + 1; g < GB; ++g) sweep(k, g);
+    }
+    return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+/*
+ * qrb200.h -- C ABI of libqrb200.so: B200-native (sm_100a) tiled Householder QR.
+ *
+ * Drop-in boundary for the GPU path of s10m/GPU-Tiled-QR-Decomposition.  The four
+ * legacy symbols of the reference's include/gpucalc.h are re-exported with the same
+ * signatures (see include/gpucalc.h in this repo); the b200qr_* entry points are the
+ * extended, device-pointer interface the legacy calls are thin wrappers over.
+ *
+ * Conventions (identical to the reference, qrdecomp.c:18 / gpucalc.cu:9):
+ *   - matrices are column-major float32, element (i,j) at mat[j*ldm + i];
+ *   - the tile size is 32 (baked into the reference, gpucalc.cu:1582, qrdecomp.c:506);
+ *     m and n must be multiples of 32; p = m/32 tile rows, q = n/32 tile columns;
+ *   - output, in place: R in the global upper triangle; strict lower part of diagonal
+ *     tile (k,k) = GEQRT reflectors (unit diagonal implied); every tile (i,k), i>k,
+ *     = the full 32x32 TSQRT reflector block V2 (reference rows a1-a4 of SURVEY 8);
+ *   - tau: one scalar per reflector, tau = 2/(1+|v_ess|^2).  The reference keeps it in
+ *     an m x n matrix whose tile (i,k) holds tau_0..tau_31 in rows 0..31 of the tile's
+ *     first column (qrdecomp.c:486,686).  This library stores it compactly,
+ *     tau_c[(k*p + i)*32 + r], and b200qr_tau_to_reference() expands it.
+ *
+ * All functions return 0 (B200QR_OK) or a negative B200QR_E* code; none prints,
+ * none resets the device.  No torch types: plain pointers and sizes only.
+ */
+#ifndef QRB200_H
+#define QRB200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200QR_TILE 32
+
+enum {
+    B200QR_OK = 0,
+    B200QR_EINVAL = -1,      /* bad shape / pointer / option                       */
+    B200QR_ECUDA = -2,       /* a CUDA runtime call failed (b200qr_last_cuda_error) */
+    B200QR_ENOMEM = -3,
+    B200QR_ESTALL = -4       /* persistent scheduler watchdog saw no progress       */
+};
+
+/* Task vocabulary of the reference (include/gridscheduler.h:10-17). */
+enum { B200QR_QRS = 0, B200QR_SAPP = 1, B200QR_QRD = 2, B200QR_DAPP = 3 };
+enum { B200QR_TASK_AVAIL = 0, B200QR_TASK_NONE = 1, B200QR_TASK_DONE = 2 };
+
+typedef struct {
+    int type;   /* B200QR_QRS .. B200QR_DAPP          (Task.taskType) */
+    int l;      /* tile row                            (Task.l)        */
+    int m;      /* tile column                         (Task.m)        */
+    int k;      /* step                                (Task.k)        */
+} b200qr_task;
+
+typedef struct {
+    int grid_ctas;      /* persistent grid size; 0 = all co-resident CTAs of the device     */
+    int trace;          /* 1 = record a per-tile-task start/finish sequence (DAG tests)      */
+    int reserved[6];
+} b200qr_opts;
+
+typedef struct b200qr_plan_s *b200qr_plan_t;
+
+/* ---- library / device info ------------------------------------------------------ */
+int         b200qr_version(void);
+const char *b200qr_strerror(int code);
+int         b200qr_last_cuda_error(void);        /* cudaError_t of the last B200QR_ECUDA */
+int         b200qr_device_sm_count(void);
+/* Measured FP32 FFMA throughput of the current device in GFLOP/s (register-resident FMA loop
+ * on every SM, best of 3 after a warm-up): the roofline denominator of the SIMT kernels.   */
+int         b200qr_measure_fp32_peak(double *gflops, int iters);
+
+/* ---- plan: workspace + schedule for one (m, n) shape ----------------------------
+ * Replaces the per-call cudaMalloc of task grid / queue / tau in cudaQRTask
+ * (gpucalc.cu:1601-1612).  A plan owns: per-tile progress words (the dependency
+ * counters), compact tau, the step table of the persistent scheduler.             */
+int  b200qr_plan_create(b200qr_plan_t *plan, int m, int n, const b200qr_opts *opts);
+int  b200qr_plan_destroy(b200qr_plan_t plan);
+int  b200qr_plan_grid(b200qr_plan_t plan);               /* CTAs the kernel launches with */
+long b200qr_plan_tile_tasks(b200qr_plan_t plan);         /* sum_k (p-k)(q-k)  (gpucalc.cu:1546-1559) */
+long b200qr_plan_macro_tasks(b200qr_plan_t plan);        /* panel + column-sweep tasks actually queued */
+
+/* ---- the hot path: factor a device-resident matrix in place ---------------------
+ * Replaces taskKernel + cuda_initScheduling (gpucalc.cu:1466-1544, launched at
+ * 1627/1638).  dA: device pointer, column-major, ldm >= m, ldm % 4 == 0, 16-byte
+ * aligned.  Asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ * default stream).  One persistent kernel launch + one small memset per call.      */
+int b200qr_factor_device(b200qr_plan_t plan, float *dA, int ldm, void *stream);
+
+/* Compact tau (device pointer owned by the plan, p*min(p,q)*32 floats). */
+const float *b200qr_plan_tau_device(b200qr_plan_t plan);
+/* Expand compact tau into the reference's m x n tau-matrix layout (device, ld = ldtau);
+ * entries outside the tau vectors are set to 0 (qrdecomp.c:90 pre-zeroes them). */
+int b200qr_tau_to_reference(b200qr_plan_t plan, float *dTauMat, int ldtau, void *stream);
+
+/* Host-buffer convenience: H2D, factor, D2H (what cudaQRTask does, gpucalc.cu:1614-1670)
+ * without the prints and without cudaDeviceReset.  hTauMat may be NULL; if given it
+ * receives tau in the reference layout (leading dimension ldm).  Synchronous.
+ * kernel_ms (optional) receives the device time of the factorisation only.         */
+int b200qr_factor_host(float *hA, int m, int n, int ldm, float *hTauMat, float *kernel_ms);
+
+/* ---- trace of the device scheduler (opts.trace = 1) -------------------------------
+ * For every tile task (k, i, j) the kernel records a global sequence number when the
+ * task starts reading its inputs and when its outputs are published.  Records come
+ * back as n x 6 ints: type, l, m, k, start_seq, finish_seq (n = tile task count). */
+int b200qr_plan_read_trace(b200qr_plan_t plan, int *out6, long cap);
+
+/* ---- single tile tasks (per-kernel parity tests; doATask, qrdecomp.c:377-449) ------
+ * Runs ONE task of the reference's vocabulary on device memory with the reference's
+ * pointer arithmetic: mat and tauMat are m x n device matrices with leading dimension
+ * ldm (tauMat in the reference tau-matrix layout).  Synchronous.                    */
+int b200qr_tile_task(int type, int l, int m, int k, float *dMat, float *dTauMat, int ldm);
+
+/* ---- host mirror of the tile-DAG scheduler (gridscheduler.h:19-21) ----------------
+ * Progress-word formulation used by the device scheduler: prog[l][m] = number of
+ * completed steps of tile (l,m); a task is ready when its tile's word equals k and the
+ * words it depends on have passed k.  Driven serially with the reference's pick rule
+ * (highest row, then highest column) it emits gridscheduler.c's exact sequence.    */
+typedef struct b200qr_sched_s *b200qr_sched_t;
+b200qr_sched_t b200qr_sched_init(int M, int N);                    /* initScheduler  */
+int  b200qr_sched_next(b200qr_sched_t s, b200qr_task *out);        /* getNextTask    */
+void b200qr_sched_done(b200qr_sched_t s, const b200qr_task *t);    /* doneATask      */
+void b200qr_sched_free(b200qr_sched_t s);
+int  b200qr_sched_progress(b200qr_sched_t s, int l, int m);        /* prog[l][m]     */
+int  b200qr_sched_ready_count(b200qr_sched_t s);
+int  b200qr_sched_dep_count(int type, int k);   /* initial dependency counter of a task */
+/* Predecessors of task t (at most 3); returns how many were written to pred[].      */
+int  b200qr_sched_predecessors(const b200qr_task *t, b200qr_task pred[3]);
+/* The device kernel's macro-task order expanded to tile tasks (n x 4 ints: type,l,m,k):
+ * ticket order of the persistent scheduler for an M x N tile grid.                  */
+long b200qr_sched_device_order(int M, int N, int *out4, long cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QRB200_H */
