@@ -18,13 +18,13 @@ TASK_AVAIL, TASK_NONE, TASK_DONE = 0, 1, 2
 # every symbol include/qrb200.h and include/gpucalc_compat.h declare
 EXPORTS = (
     "b200qr_version", "b200qr_strerror", "b200qr_last_cuda_error", "b200qr_device_sm_count",
-    "b200qr_measure_fp32_peak",
+    "b200qr_measure_fp32_peak", "b200qr_probe_panel",
     "b200qr_plan_create", "b200qr_plan_destroy", "b200qr_plan_grid", "b200qr_plan_tile_tasks",
     "b200qr_plan_macro_tasks", "b200qr_factor_device", "b200qr_plan_tau_device",
     "b200qr_tau_to_reference", "b200qr_factor_host", "b200qr_plan_read_trace", "b200qr_tile_task",
     "b200qr_sched_init", "b200qr_sched_next", "b200qr_sched_done", "b200qr_sched_free",
     "b200qr_sched_progress", "b200qr_sched_ready_count", "b200qr_sched_dep_count",
-    "b200qr_sched_predecessors", "b200qr_sched_device_order",
+    "b200qr_sched_predecessors", "b200qr_sched_device_order", "b200qr_sched_sweep_order",
     "cudaQRTask", "cudaQRFull", "testDAPP", "doCUDADAPP",
 )
 
@@ -69,6 +69,7 @@ def lib():
         L.b200qr_strerror.restype = C.c_char_p
         L.b200qr_strerror.argtypes = [C.c_int]
         L.b200qr_measure_fp32_peak.argtypes = [C.POINTER(C.c_double), C.c_int]
+        L.b200qr_probe_panel.argtypes = [C.POINTER(C.c_longlong), C.c_int]
         L.b200qr_plan_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(Opts)]
         L.b200qr_plan_destroy.argtypes = [vp]
         L.b200qr_plan_grid.argtypes = [vp]
@@ -94,6 +95,8 @@ def lib():
         L.b200qr_sched_predecessors.argtypes = [C.POINTER(Task), C.POINTER(Task)]
         L.b200qr_sched_device_order.argtypes = [C.c_int, C.c_int, vp, C.c_long]
         L.b200qr_sched_device_order.restype = C.c_long
+        L.b200qr_sched_sweep_order.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.c_long]
+        L.b200qr_sched_sweep_order.restype = C.c_long
         L.cudaQRTask.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
         L.cudaQRTask.restype = None
         L.cudaQRFull.argtypes = [vp, C.c_int, C.c_int]
@@ -120,7 +123,7 @@ class Plan:
         self.m, self.n = m, n
         self._h = C.c_void_p()
         o = Opts()
-        o.grid_ctas, o.trace = int(grid_ctas), int(bool(trace))
+        o.grid_ctas, o.trace = int(grid_ctas), int(trace)
         check(lib().b200qr_plan_create(C.byref(self._h), m, n, C.byref(o)), "b200qr_plan_create")
 
     @property

@@ -11,6 +11,7 @@
 // engine) completing on mbarriers; each thread moves its own 128-byte column.
 #pragma once
 #include <cstdint>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 namespace qrb200 {
@@ -28,6 +29,13 @@ __device__ __forceinline__ int ld_acquire(const int *p)
 {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// plain L2 poll (LDG.STRONG.GPU, no L1 invalidate); pair with one __threadfence() after the loop
+__device__ __forceinline__ int ld_relaxed(const int *p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_release(int *p, int v)
@@ -85,6 +93,30 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u
                  "r"(smem_u32(src_smem)), "r"(bytes)
                  : "memory");
 }
+// TMA: 2-D tiled tensor copies (SASS: UTMALDG / UTMASTG).  c0 = row (inner), c1 = column.
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, const void *src_smem)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(c0), "r"(c1), "r"(smem_u32(src_smem))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
@@ -102,6 +134,28 @@ __device__ __forceinline__ void store_col_smem(float *col, const float (&x)[TB])
     for (int r = 0; r < TB; r += 4)
         *reinterpret_cast<float4 *>(col + r) = make_float4(x[r], x[r + 1], x[r + 2], x[r + 3]);
 }
+// A 32x32 fp32 tile landed by TMA with CU_TENSOR_MAP_SWIZZLE_128B: matrix column c is the 128-byte
+// line c of the (1024-byte aligned) tile, and its 16-byte chunk i sits at chunk slot i ^ (c & 7).
+// A thread that owns column `lane` therefore reads 8 x LDS.128 with no bank conflicts.
+__device__ __forceinline__ void load_col_sw(float (&x)[TB], const float *tile, int lane)
+{
+    const char *base = reinterpret_cast<const char *>(tile) + lane * 128;
+    const int sw = (lane & 7) << 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float4 t = *reinterpret_cast<const float4 *>(base + ((i << 4) ^ sw));
+        x[4 * i] = t.x; x[4 * i + 1] = t.y; x[4 * i + 2] = t.z; x[4 * i + 3] = t.w;
+    }
+}
+__device__ __forceinline__ void store_col_sw(float *tile, int lane, const float (&x)[TB])
+{
+    char *base = reinterpret_cast<char *>(tile) + lane * 128;
+    const int sw = (lane & 7) << 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4 *>(base + ((i << 4) ^ sw)) =
+            make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+}
 __device__ __forceinline__ void load_col_gmem(float (&x)[TB], const float *col)
 {
 #pragma unroll
@@ -117,66 +171,76 @@ __device__ __forceinline__ void store_col_gmem(float *col, const float (&x)[TB])
         *reinterpret_cast<float4 *>(col + r) = make_float4(x[r], x[r + 1], x[r + 2], x[r + 3]);
 }
 
+// ------------------------------------------------------------------ panel kernels: shared pieces
+// Householder scalars from the head element x0 and the sum of squares of the rest, restating
+// calcvkSingle / calcvkDouble + the tau of updateSingleQ_WY / updateDoubleQ_WY
+// (qrdecomp.c:1201-1272, 498-504, 660-664):
+//   nrm = sqrt(x0^2 + ssq);  piv = x0 + sign(x0) nrm (sign(0) = +1);  v = x / piv;
+//   tau = 2 / (1 + |v_ess|^2)  ==  |piv| / nrm  ==  1 + |x0| / nrm      (exact identity),
+// so one reciprocal square root gives nrm and tau, and 1/piv does not wait for a second
+// division.  nrm == 0 leaves v unscaled and tau = 2, like the reference (qrdecomp.c:1219).
+struct HouseScalars { float inv, tau; };
+__device__ __forceinline__ HouseScalars house_scalars(float x0, float ssq)
+{
+    const float nsq = fmaf(x0, x0, ssq);
+    float rn = rsqrtf(nsq);
+    rn = rn * fmaf(-0.5f * nsq * rn, rn, 1.5f);            // one Newton step: ~1 ulp
+    const float nrm = nsq * rn;
+    const float piv = x0 + (x0 >= 0.f ? nrm : -nrm);
+    HouseScalars h;
+    const bool degenerate = !(nsq > 0.f);
+    h.inv = degenerate ? 1.0f : __frcp_rn(piv);
+    h.tau = degenerate ? 2.0f : fmaf(fabsf(x0), rn, 1.0f);
+    return h;
+}
+// 8 independent accumulators: 4-deep FMA chains instead of 32-deep
+__device__ __forceinline__ float dot32(const float (&a)[TB], const float (&x)[TB])
+{
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = a[i] * x[i];
+#pragma unroll
+    for (int r = 8; r < TB; r += 8)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] = fmaf(a[r + i], x[r + i], s[i]);
+    return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+}
+// one lane's 32 floats -> every lane, through a 128-byte shared-memory slot
+__device__ __forceinline__ void bcast_col(float (&x)[TB], const float (&mine)[TB], float *slot, bool owner)
+{
+    if (owner) store_col_smem(slot, mine);
+    __syncwarp();
+    load_col_smem(x, slot);
+}
+
 // ------------------------------------------------------------------ a1: GEQRT ("QRS")
 // Householder QR of one 32x32 tile held by a warp, lane = column (reference semantics:
 // qrdecomp.c:532-557 SGEQRF, 1201-1227 calcvkSingle, 489-530 updateSingleQ_WY).
 // On exit a[] holds R on/above the diagonal and the reflector below it; the return value
-// of lane c is tau_c = 2/(1+|v_ess|^2).
-__device__ __forceinline__ float geqrt_warp(float (&a)[TB], int lane)
+// of lane c is tau_c.  xs: 64 floats of shared-memory scratch (16-byte aligned).
+__device__ __forceinline__ float geqrt_warp(float (&a)[TB], float *xs, int lane)
 {
     float my_tau = 0.f;
 #pragma unroll 1
     for (int c = 0; c < TB; ++c) {
-        // |x|^2 of this lane's column from row c down, and its head element x_c
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, head = 0.f;
-#pragma unroll
-        for (int r = 0; r < TB; r += 4) {
-            float y0 = (r + 0 >= c) ? a[r + 0] : 0.f;
-            float y1 = (r + 1 >= c) ? a[r + 1] : 0.f;
-            float y2 = (r + 2 >= c) ? a[r + 2] : 0.f;
-            float y3 = (r + 3 >= c) ? a[r + 3] : 0.f;
-            s0 = fmaf(y0, y0, s0); s1 = fmaf(y1, y1, s1);
-            s2 = fmaf(y2, y2, s2); s3 = fmaf(y3, y3, s3);
-            head = (r + 0 == c) ? a[r + 0] : head;
-            head = (r + 1 == c) ? a[r + 1] : head;
-            head = (r + 2 == c) ? a[r + 2] : head;
-            head = (r + 3 == c) ? a[r + 3] : head;
-        }
-        float ssq = (s0 + s1) + (s2 + s3);
-        // only column c defines the reflector
-        ssq = __shfl_sync(FULL, ssq, c);
-        head = __shfl_sync(FULL, head, c);
-        float nrm = sqrtf(ssq);
-        float piv = head + (head >= 0.f ? nrm : -nrm);      // x_c + sign(x_c)|x|, sign(0)=+1 (qrdecomp.c:1208)
-        float inv = (nrm != 0.f) ? 1.0f / piv : 1.0f;       // |x|==0: left unscaled (qrdecomp.c:1219)
-        // v = [0 .. 0, 1, x_{c+1..}/piv], broadcast from lane c
+        float x[TB];
+        bcast_col(x, a, xs + (c & 1) * TB, lane == c);       // column c as it stands now
+        const float head = xs[(c & 1) * TB + c];
         float v[TB];
-        float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
-        for (int r = 0; r < TB; ++r) {
-            float xr = __shfl_sync(FULL, a[r], c);
-            v[r] = (r > c) ? xr * inv : ((r == c) ? 1.0f : 0.f);
-        }
+        for (int r = 0; r < TB; ++r) v[r] = (r > c) ? x[r] : 0.f;
+        const HouseScalars h = house_scalars(head, dot32(v, v));
+        // v = [0 .. 0, 1, x_{c+1..}/piv]
 #pragma unroll
-        for (int r = 0; r < TB; r += 4) {
-            q0 = fmaf(v[r], v[r], q0); q1 = fmaf(v[r + 1], v[r + 1], q1);
-            q2 = fmaf(v[r + 2], v[r + 2], q2); q3 = fmaf(v[r + 3], v[r + 3], q3);
-        }
-        float scale = -2.0f / ((q0 + q1) + (q2 + q3));       // -tau_c
-        // A(:, j) += scale * v * (v' A(:, j)) for j >= c
-        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-#pragma unroll
-        for (int r = 0; r < TB; r += 4) {
-            d0 = fmaf(a[r], v[r], d0); d1 = fmaf(a[r + 1], v[r + 1], d1);
-            d2 = fmaf(a[r + 2], v[r + 2], d2); d3 = fmaf(a[r + 3], v[r + 3], d3);
-        }
-        float f = (lane >= c) ? scale * ((d0 + d1) + (d2 + d3)) : 0.f;
+        for (int r = 0; r < TB; ++r) v[r] = (r > c) ? v[r] * h.inv : ((r == c) ? 1.0f : 0.f);
+        // A(:, j) -= tau v (v' A(:, j)) for j >= c
+        const float f = (lane >= c) ? -h.tau * dot32(a, v) : 0.f;
 #pragma unroll
         for (int r = 0; r < TB; ++r) a[r] = fmaf(f, v[r], a[r]);
         if (lane == c) {
 #pragma unroll
             for (int r = 0; r < TB; ++r) a[r] = (r > c) ? v[r] : a[r];
-            my_tau = -scale;
+            my_tau = h.tau;
         }
     }
     return my_tau;
@@ -186,49 +250,35 @@ __device__ __forceinline__ float geqrt_warp(float (&a)[TB], int lane)
 // QR of [R; B] with R upper triangular (kept in shared memory, Rs[row*33 + col]) and B a
 // full 32x32 tile held by the warp, lane = column (reference: qrdecomp.c:689-721 STSQRF,
 // 1243-1272 calcvkDouble, 647-687 updateDoubleQ_WY).  On exit b[] holds V2, Rs the new R,
-// lane c returns tau_c.
-__device__ __forceinline__ float tsqrt_warp(float (&b)[TB], float *Rs, int lane)
+// lane c returns tau_c.  The serial chain per column is kept short: the owner lane's sum of
+// squares is ready from the previous update, the dot products use the unscaled column x (the
+// scale 1/piv is applied to the scalar), so they overlap the rsqrt / reciprocal.
+struct NoMid { __device__ __forceinline__ void operator()() const {} };
+// `mid` runs once, a quarter of the way through the tile: the persistent kernel uses it to publish
+// the PREVIOUS tile of the chain (whose TMA store has long completed by then) off the critical path.
+template <class Mid = NoMid>
+__device__ __forceinline__ float tsqrt_warp(float (&b)[TB], float *Rs, float *xs, int lane, Mid mid = Mid())
 {
     float my_tau = 0.f;
+    float ssq = dot32(b, b);
 #pragma unroll 1
     for (int c = 0; c < TB; ++c) {
-        float rc = Rs[c * 33 + lane];                         // R(c, lane)
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-        for (int r = 0; r < TB; r += 4) {
-            s0 = fmaf(b[r], b[r], s0); s1 = fmaf(b[r + 1], b[r + 1], s1);
-            s2 = fmaf(b[r + 2], b[r + 2], s2); s3 = fmaf(b[r + 3], b[r + 3], s3);
-        }
-        float ssq = (s0 + s1) + (s2 + s3);
-        float diag = __shfl_sync(FULL, rc, c);
-        ssq = __shfl_sync(FULL, ssq, c);
-        float nrm = sqrtf(fmaf(diag, diag, ssq));
-        float piv = diag + (diag >= 0.f ? nrm : -nrm);
-        float inv = (nrm != 0.f) ? 1.0f / piv : 1.0f;
-        float v[TB];
-#pragma unroll
-        for (int r = 0; r < TB; ++r) v[r] = __shfl_sync(FULL, b[r], c) * inv;
-        float q0 = 1.0f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-#pragma unroll
-        for (int r = 0; r < TB; r += 4) {
-            q0 = fmaf(v[r], v[r], q0); q1 = fmaf(v[r + 1], v[r + 1], q1);
-            q2 = fmaf(v[r + 2], v[r + 2], q2); q3 = fmaf(v[r + 3], v[r + 3], q3);
-        }
-        float t = 2.0f / ((q0 + q1) + (q2 + q3));
-        float d0 = rc, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-#pragma unroll
-        for (int r = 0; r < TB; r += 4) {
-            d0 = fmaf(b[r], v[r], d0); d1 = fmaf(b[r + 1], v[r + 1], d1);
-            d2 = fmaf(b[r + 2], v[r + 2], d2); d3 = fmaf(b[r + 3], v[r + 3], d3);
-        }
-        float beta = (lane >= c) ? t * ((d0 + d1) + (d2 + d3)) : 0.f;
+        if (c == 8) mid();
+        const float rc = Rs[c * 33 + lane];                   // R(c, lane)
+        float x[TB];
+        bcast_col(x, b, xs + (c & 1) * TB, lane == c);        // x = B(:, c)
+        const HouseScalars h = house_scalars(__shfl_sync(FULL, rc, c), __shfl_sync(FULL, ssq, c));
+        // beta = tau (R(c,j) + v' B(:,j)),  v = x / piv
+        const float beta = (lane >= c) ? h.tau * fmaf(h.inv, dot32(b, x), rc) : 0.f;
         Rs[c * 33 + lane] = rc - beta;
+        const float g = (lane > c) ? -beta * h.inv : 0.f;
 #pragma unroll
-        for (int r = 0; r < TB; ++r) b[r] = fmaf(-beta, v[r], b[r]);
+        for (int r = 0; r < TB; ++r) b[r] = fmaf(g, x[r], b[r]);
+        ssq = dot32(b, b);                                    // needed from lane c+1 next step
         if (lane == c) {
 #pragma unroll
-            for (int r = 0; r < TB; ++r) b[r] = v[r];
-            my_tau = t;
+            for (int r = 0; r < TB; ++r) b[r] = x[r] * h.inv;
+            my_tau = h.tau;
         }
     }
     return my_tau;
@@ -265,6 +315,56 @@ __device__ __forceinline__ void apply_block_reflectors(float (&b)[TB], float *to
         if (HAS_TOP) top[c * top_stride] = a0 - beta;
 #pragma unroll
         for (int r = 0; r < TB; ++r) b[r] = fmaf(-beta, v[r], b[r]);
+    }
+}
+
+// Same operation on NC (1 or 2) columns held by one thread (the persistent kernel's sweep
+// consumers): the reflector is read from shared memory once and applied to NC independent
+// columns, which also gives the FMA pipe NC independent dependency chains.  top0/top1 point at
+// this thread's entries of the resident tile row (element c at top[c*top_rs]).
+// HAS_TOP = false takes the raw diagonal tile (R above the diagonal) and substitutes the
+// implied zeros / unit diagonal on the fly (UNMQR, qrdecomp.c:620-644).
+template <int NC, bool HAS_TOP>
+__device__ __forceinline__ void apply_reflectors_nc(float (&b0)[TB], float (&b1)[TB], float *top0, float *top1,
+                                                    int top_rs, const float *vs, const float *ts)
+{
+#pragma unroll 2
+    for (int c = 0; c < TB; ++c) {
+        float v[TB];
+        load_col_smem(v, vs + c * TB);
+        if (!HAS_TOP) {
+#pragma unroll
+            for (int r = 0; r < TB; ++r) v[r] = (r > c) ? v[r] : ((r == c) ? 1.0f : 0.f);
+        }
+        const float tc = ts[c];
+        {
+            float a0 = 0.f;
+            if (HAS_TOP) a0 = top0[c * top_rs];
+            float d0 = a0, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+            for (int r = 0; r < TB; r += 4) {
+                d0 = fmaf(b0[r], v[r], d0); d1 = fmaf(b0[r + 1], v[r + 1], d1);
+                d2 = fmaf(b0[r + 2], v[r + 2], d2); d3 = fmaf(b0[r + 3], v[r + 3], d3);
+            }
+            const float beta = tc * ((d0 + d1) + (d2 + d3));
+            if (HAS_TOP) top0[c * top_rs] = a0 - beta;
+#pragma unroll
+            for (int r = 0; r < TB; ++r) b0[r] = fmaf(-beta, v[r], b0[r]);
+        }
+        if (NC == 2) {
+            float a0 = 0.f;
+            if (HAS_TOP) a0 = top1[c * top_rs];
+            float d0 = a0, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+            for (int r = 0; r < TB; r += 4) {
+                d0 = fmaf(b1[r], v[r], d0); d1 = fmaf(b1[r + 1], v[r + 1], d1);
+                d2 = fmaf(b1[r + 2], v[r + 2], d2); d3 = fmaf(b1[r + 3], v[r + 3], d3);
+            }
+            const float beta = tc * ((d0 + d1) + (d2 + d3));
+            if (HAS_TOP) top1[c * top_rs] = a0 - beta;
+#pragma unroll
+            for (int r = 0; r < TB; ++r) b1[r] = fmaf(-beta, v[r], b1[r]);
+        }
     }
 }
 

@@ -6,20 +6,28 @@
 //
 // Scheduler.  The tile DAG of the reference (gridscheduler.c:112-174) is tracked with one
 // 32-bit progress word per tile, prog[j*p + i] = number of completed steps of tile (i,j) --
-// the reference's (k, taskStatus) pair collapsed.  Work is handed out as
-// MACRO TASKS through a single atomic ticket counter, in an order that is a topological
-// order of the DAG:
-//     P(k)   "panel":  GEQRT(k,k) then the TSQRT chain (i,k), i = k+1..p-1      (1 warp)
-//     S(k,g) "sweep":  for the G tile columns of group g: UNMQR(k,j) then the TSMQR
-//                      chain (i,j), i = k+1..p-1, with tile row k resident on chip.
-//   tickets: P(0); then per step k:  S(k,g0)  P(k+1)  S(k,g0+1)  S(k,g0+2) ...
-// (g0 = group holding tile column k+1, so the next panel's column is updated first:
-// look-ahead).  A CTA that holds a ticket waits, tile row by tile row, on the progress
-// words of its predecessors (ld.acquire.gpu spin) and publishes its own with st.release.gpu.
-// Because every dependency points to an earlier ticket and all CTAs are co-resident
-// (cooperative launch), the oldest unfinished ticket can always run: no deadlock, no
-// queue, no locks, no host round trips.  Panels of successive steps and the sweeps behind
-// them pipeline as a wavefront down the matrix.
+// the reference's (k, taskStatus) pair collapsed.  Work is handed out as MACRO
+// TASKS through two atomic ticket counters, each in an order that is a topological order of
+// the DAG:
+//     P(k)   "panel":  GEQRT(k,k) then the TSQRT chain (i,k), i = k+1..p-1   -- panel warp
+//     S(k,g) "sweep":  for the G tile columns of group g: UNMQR(k,j) then the TSMQR chain
+//                      (i,j), i = k+1..p-1, with tile row k resident on chip  -- sweep warps
+//   panel tickets: P(0) P(1) P(2) ...;  sweep tickets: per step k, S(k,g0) S(k,g0+1) ...
+//   (g0 = group holding tile column k+1, so the next panel's column is updated first).
+// Every CTA runs BOTH streams at once: one panel warp, and a warp-specialised sweep engine
+// (loader warp -> consumer warps -> storer warp, connected by shared-memory mbarriers):
+//   loader   polls the progress words of the next tile row (one relaxed L2 load per lane, one
+//            fence when they are all there), then TMA-loads the row's tiles, the reflector
+//            tile and its tau into a stage of the ring;
+//   consumer one thread owns NC matrix columns (32 floats each in registers) and applies the 32
+//            reflectors of the row's TSQRT one after another, exactly the reference's operation
+//            sequence (qrdecomp.c:736-762), reading V with 128-bit broadcast loads;
+//   storer   TMA-stores the updated tiles, waits for the store, fences and publishes the tiles'
+//            progress words with st.release -- off the consumers' critical path.
+// Dependencies always point to an earlier ticket of one of the two streams and every CTA is
+// co-resident (cooperative launch), so the oldest unfinished ticket of each stream can always
+// run: no deadlock, no queue, no locks, no host round trips.  A sweep is sized (G tile columns)
+// so that one tile row of it takes about as long as one TSQRT of the panel chain it follows.
 #include "qr_device.cuh"
 #include "../../include/qrb200.h"
 
@@ -30,37 +38,57 @@
 
 namespace qrb200 {
 
-constexpr int G = 4;                  // tile columns per sweep task (one warp each)
-constexpr int NT = 32 * G;            // threads per CTA
+constexpr int CW = 8;                         // consumer warps per CTA
+constexpr int NPW = 2;                        // panel warps per CTA (one TSQRT chain each)
+constexpr int NTHREADS = (CW + 2 + NPW) * 32; // + loader, storer, panel warps
+constexpr int SWEEP_THREADS = (CW + 2) * 32;  // threads that share a sweep ticket
+constexpr int W_LOADER = CW, W_STORER = CW + 1, W_PANEL = CW + 2;
+constexpr int TILE_BYTES = TB * TB * 4;
 
 struct Params {
     float *A;
     int ldm, p, q, K;
-    float *tauc;          // compact tau: [(k*p + i)*32 + r]
-    int *prog;            // progress words: [j*p + i]
-    int *ctr;             // [0] ticket counter, [1] trace sequence counter
-    const int *step_start;  // K+1 entries: first ticket of step k (ticket 0 is P(0))
-    int ntickets;
-    int *trace;           // optional: 2 ints (start, finish sequence) per tile task
+    float *tauc;              // compact tau: [(k*p + i)*32 + r]
+    int *prog;                // progress words: [j*p + i]
+    int *ctr;                 // [0] sweep tickets, [1] trace sequence, [2] panel tickets
+    const int2 *sweep_tab;    // sweep ticket -> (k, g), in the skewed order of b200qr_sched_sweep_order()
+    int nsweeps;
+    int npanel_ctas;          // > 0: role split -- CTAs [0, npanel_ctas) run only panel warps, the rest only sweeps;
+                              // 0: every CTA runs both (small grids; NC = 1 only)
+    int trace_mode;           // 1 = global sequence numbers, 2 = low 32 bits of %globaltimer (ns)
+    int *trace;               // optional: 2 ints (start, finish) per tile task
     const long long *trace_off;  // K entries: first trace slot of step k
     unsigned long long watchdog_ns;
 };
 
-struct __align__(16) Smem {
-    uint64_t sfull[2];    // sweep stage barriers (NT arrivals)
-    uint64_t pfull[2];    // panel stage barriers (32 arrivals)
-    union {
-        struct {
-            float col[2][NT][COL_STRIDE];   // staged tile columns, double buffered
-            float top[TB][NT];              // tile row k of this column group (resident)
-            float v[2][TB * TB];            // reflector block of the current tile row
-            float tau[2][TB];
-        } s;
-        struct {
-            float col[2][TB][COL_STRIDE];
-            float Rs[TB * 33];
-        } p;
-    } u;
+template <int NC>
+struct Cfg {
+    static constexpr int G = CW * NC;                 // tile columns per sweep
+    static constexpr int NS = NC == 1 ? 3 : 2;        // ring stages
+    static constexpr int STAGE_BYTES = (G + 1) * TILE_BYTES + 1024;   // tiles, V, tau (+pad)
+    static constexpr int OFF_TOP = NS * STAGE_BYTES;
+    static constexpr int SWEEP_END = OFF_TOP + G * TILE_BYTES;
+    // per panel warp: 2 input tiles, 1 output tile, R (33-float rows) + broadcast slots.  The NC = 2
+    // variant only runs role-split (a CTA is either a panel CTA or a sweep CTA), so its panel region
+    // overlays the sweep stages; NC = 1 keeps them apart and can run both roles in one CTA.
+    static constexpr int PANEL_BYTES = 3 * TILE_BYTES + 5120;
+    static constexpr int OFF_PANEL = NC == 2 ? 0 : SWEEP_END;
+    static constexpr int OFF_BAR = NC == 2 ? SWEEP_END : SWEEP_END + NPW * PANEL_BYTES;
+    static constexpr int SMEM_BYTES = OFF_BAR + 256;
+};
+
+// The CTA's dynamic shared memory (no static __shared__ in this kernel, so it starts at offset 0
+// of the CTA's window: 1024-byte aligned as the 128B-swizzled TMA tiles need).  Every access goes
+// through this symbol so the compiler keeps the shared address space (LDS/STS, not generic LD/ST).
+extern __shared__ __align__(1024) unsigned char g_smem[];
+
+struct Ring {
+    int stage = 0;
+    uint32_t phase = 0;
+    template <int NS> __device__ __forceinline__ void advance()
+    {
+        if (++stage == NS) { stage = 0; phase ^= 1; }
+    }
 };
 
 __device__ __forceinline__ unsigned long long gtimer()
@@ -70,16 +98,27 @@ __device__ __forceinline__ unsigned long long gtimer()
     return t;
 }
 
-// Spin until *p >= target.  A scheduler bug must not hang the GPU: after watchdog_ns of
-// kernel time the kernel traps (host sees a launch failure -> B200QR_ESTALL).
-__device__ __forceinline__ void wait_ge(const int *p, int target, unsigned long long t0, unsigned long long limit)
-{
-    if (ld_acquire(p) >= target) return;
-    unsigned spins = 0;
-    while (ld_acquire(p) < target) {
-        __nanosleep(64);
-        if (((++spins) & 0xfffu) == 0 && gtimer() - t0 > limit) __trap();
+struct Watch {
+    unsigned long long t0, limit;
+    __device__ __forceinline__ void check(unsigned &spins) const
+    {
+        if (((++spins) & 0x3fffu) == 0 && gtimer() - t0 > limit) __trap();
     }
+};
+
+// A scheduler bug must not hang the GPU: every wait is bounded by the watchdog, which traps
+// the kernel (host sees a launch failure -> B200QR_ESTALL).
+__device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, const Watch &w)
+{
+    unsigned spins = 0;
+    while (!mbar_try_wait(bar, parity)) w.check(spins);
+}
+// Spin (whole warp, one coalesced L2 load per iteration) until *p >= target, then acquire.
+__device__ __forceinline__ void wait_flag(const int *p, int target, const Watch &w)
+{
+    unsigned spins = 0;
+    while (ld_relaxed(p) < target) { __nanosleep(32); w.check(spins); }
+    __threadfence();
 }
 
 __device__ __forceinline__ long long trace_slot(const Params &P, int k, int i, int j)
@@ -88,205 +127,313 @@ __device__ __forceinline__ long long trace_slot(const Params &P, int k, int i, i
 }
 __device__ __forceinline__ void trace_mark(const Params &P, int k, int i, int j, int which)
 {
-    if (P.trace) P.trace[2 * trace_slot(P, k, i, j) + which] = atomicAdd(&P.ctr[1], 1);
+    if (P.trace)
+        P.trace[2 * trace_slot(P, k, i, j) + which] =
+            P.trace_mode == 2 ? (int)(unsigned)gtimer() : atomicAdd(&P.ctr[1], 1);
 }
 
-// ------------------------------------------------------------------ P(k): panel, warp 0
-__device__ void run_panel(const Params &P, int k, Smem &sm, uint32_t (&ph)[2], unsigned long long t0)
+// ------------------------------------------------------------------ P(k): the panel warp
+template <int NC>
+__device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int pw, uint32_t &phbits, const Watch &wd)
 {
+    using C = Cfg<NC>;
     const int lane = threadIdx.x & 31;
     const int p = P.p;
-    float *colbase = P.A + (size_t)(k * TB + lane) * P.ldm;   // my column of tile column k
+    unsigned char *mine = g_smem + C::OFF_PANEL + pw * C::PANEL_BYTES;
+    float *pin0 = reinterpret_cast<float *>(mine);                      // 2 input slots, TB*TB floats apart
+    float *pout = reinterpret_cast<float *>(mine + 2 * TILE_BYTES);
+    float *Rs = reinterpret_cast<float *>(mine + 3 * TILE_BYTES);
+    float *xs = reinterpret_cast<float *>(mine + 3 * TILE_BYTES + 4352);   // 2 x 128 B broadcast slots
+    uint64_t *pfull = reinterpret_cast<uint64_t *>(g_smem + C::OFF_BAR) + 3 * C::NS + 2 * pw;
     int *prog_col = P.prog + (size_t)k * p;
     float *tauc = P.tauc + (size_t)k * p * TB;
 
-    auto issue = [&](int row, int s) {
-        fence_proxy_async();
-        mbar_arrive_expect_tx(&sm.pfull[s], 128);
-        bulk_g2s(&sm.u.p.col[s][lane][0], colbase + row * TB, 128, &sm.pfull[s]);
+    auto issue = [&](int row, int s) {               // TMA-load tile (row, k) into input slot s
+        if (lane == 0) {
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&pfull[s], TILE_BYTES);
+            tma_load_2d(pin0 + s * TB * TB, mapA, row * TB, k * TB, &pfull[s]);
+        }
+    };
+    int pending = -1;                                // tile row whose store is in flight, unpublished
+    auto publish = [&]() {                           // wait for the store, fence, release the flag
+        if (pending >= 0) {
+            if (lane == 0) {
+                bulk_wait_all();
+                __threadfence();
+                st_release(prog_col + pending, k + 1);
+            }
+            pending = -1;
+        }
+    };
+    auto store_tile = [&](int row, const float (&x)[TB]) {   // x -> pout -> TMA store (async)
+        store_col_sw(pout, lane, x);
+        fence_proxy_async_smem();
+        __syncwarp();                                // also orders this warp's tau stores before lane 0's release
+        if (lane == 0) { tma_store_2d(mapA, row * TB, k * TB, pout); bulk_commit(); }
+        pending = row;
     };
 
     // ---- GEQRT on the diagonal tile
-    wait_ge(prog_col + k, k, t0, P.watchdog_ns);
+    wait_flag(prog_col + k, k, wd);
     issue(k, 0);
-    mbar_wait(&sm.pfull[0], ph[0]); ph[0] ^= 1;
+    mbar_wait_wd(&pfull[0], phbits & 1, wd); phbits ^= 1;
     float a[TB];
-    load_col_smem(a, sm.u.p.col[0][lane]);
+    load_col_sw(a, pin0, lane);
     if (lane == 0) trace_mark(P, k, k, k, 0);
-    float t = geqrt_warp(a, lane);
-    store_col_gmem(colbase + k * TB, a);      // reflectors final; R part rewritten after the chain
+    float t = geqrt_warp(a, xs, lane);
+    if (lane == 0) trace_mark(P, k, k, k, 1);        // result exists (on chip for the chain below; published soon)
     tauc[k * TB + lane] = t;
 #pragma unroll
-    for (int r = 0; r < TB; ++r) sm.u.p.Rs[r * 33 + lane] = a[r];
-    __threadfence();
-    __syncwarp();
-    if (lane == 0) { trace_mark(P, k, k, k, 1); st_release(prog_col + k, k + 1); }
+    for (int r = 0; r < TB; ++r) Rs[r * 33 + lane] = a[r];   // upper = R (updated by the chain), lower = V
+    store_tile(k, a);
 
     // ---- TSQRT chain down the tile column; R stays in shared memory
     bool have_cur = false;
     for (int i = k + 1; i < p; ++i) {
         const int s = (i - k) & 1;
-        if (!have_cur) { wait_ge(prog_col + i, k, t0, P.watchdog_ns); issue(i, s); }
-        bool have_next = false;
-        if (i + 1 < p && ld_acquire(prog_col + i + 1) >= k) { issue(i + 1, s ^ 1); have_next = true; }
-        mbar_wait(&sm.pfull[s], ph[s]); ph[s] ^= 1;
-        float b[TB];
-        load_col_smem(b, sm.u.p.col[s][lane]);
-        if (lane == 0) trace_mark(P, k, i, k, 0);
-        float ti = tsqrt_warp(b, sm.u.p.Rs, lane);
-        store_col_gmem(colbase + i * TB, b);
-        tauc[i * TB + lane] = ti;
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) { trace_mark(P, k, i, k, 1); st_release(prog_col + i, k + 1); }
-        have_cur = have_next;
-    }
-    // ---- final R of the diagonal tile (upper triangle only; reflectors below stay)
-#pragma unroll
-    for (int r = 0; r < TB; ++r)
-        if (r <= lane) colbase[k * TB + r] = sm.u.p.Rs[r * 33 + lane];
-}
-
-// ------------------------------------------------------------------ S(k,g): column sweep
-__device__ void run_sweep(const Params &P, int k, int g, Smem &sm, uint32_t (&ph)[2], unsigned long long t0)
-{
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int p = P.p;
-    const int jt = g * G + warp;                        // my warp's tile column
-    const bool active = jt > k && jt < P.q;
-    const int nrows = p - k;
-    float *colbase = P.A + (size_t)(active ? jt * TB + lane : 0) * P.ldm;
-    const float *vbase = P.A + (size_t)(k * TB + lane) * P.ldm;   // reflector tiles live in tile column k
-    const float *taubase = P.tauc + (size_t)k * p * TB;
-    const int *prog_panel = P.prog + (size_t)k * p;
-    int *prog_mine = P.prog + (size_t)(active ? jt : 0) * p;
-
-    auto ready = [&](int row) -> bool {
-        if (ld_acquire(prog_panel + row) < k + 1) return false;          // reflectors of (row,k) published
-        if (active && ld_acquire(prog_mine + row) < k) return false;     // my tile finished step k-1
-        return true;
-    };
-    auto issue = [&](int row, int s) {
-        uint32_t bytes = (active ? 128u : 0u) + (warp == 0 ? 128u : 0u) + (tid == 0 ? 128u : 0u);
-        fence_proxy_async();
-        if (bytes) mbar_arrive_expect_tx(&sm.sfull[s], bytes);
-        else mbar_arrive(&sm.sfull[s]);
-        if (active) bulk_g2s(&sm.u.s.col[s][tid][0], colbase + row * TB, 128, &sm.sfull[s]);
-        if (warp == 0) {
-            bulk_g2s(&sm.u.s.v[s][lane * TB], vbase + row * TB, 128, &sm.sfull[s]);
-            if (lane == 0) bulk_g2s(sm.u.s.tau[s], taubase + row * TB, 128, &sm.sfull[s]);
-        }
-    };
-
-    bool have_cur = false;
-    for (int idx = 0; idx < nrows; ++idx) {
-        const int row = k + idx, s = idx & 1;
-        __syncthreads();                                   // everyone is done with stage s^1's reflectors
         if (!have_cur) {
-            unsigned spins = 0;
-            while (!ready(row)) {
-                __nanosleep(64);
-                if (((++spins) & 0xfffu) == 0 && gtimer() - t0 > P.watchdog_ns) __trap();
-            }
-            issue(row, s);
+            if (ld_relaxed(prog_col + i) < k) publish();     // about to block: do not sit on a finished tile
+            wait_flag(prog_col + i, k, wd);
+            issue(i, s);
         }
         bool have_next = false;
-        if (idx + 1 < nrows && ready(row + 1)) { issue(row + 1, s ^ 1); have_next = true; }
-        mbar_wait(&sm.sfull[s], ph[s]); ph[s] ^= 1;
-
-        if (idx == 0) {
-            // tile row k: UNMQR with the GEQRT reflectors of the diagonal tile
-            make_unit_lower(sm.u.s.v[s], tid, NT);
-            __syncthreads();
-            if (active) {
-                float b[TB];
-                load_col_smem(b, sm.u.s.col[s][tid]);
-                if (lane == 0) trace_mark(P, k, k, jt, 0);
-                apply_block_reflectors<false>(b, nullptr, 0, sm.u.s.v[s], sm.u.s.tau[s]);
-#pragma unroll
-                for (int r = 0; r < TB; ++r) sm.u.s.top[r][tid] = b[r];
-            }
-        } else if (active) {
-            // tile row `row`: TSMQR against the resident tile row k
-            float b[TB];
-            load_col_smem(b, sm.u.s.col[s][tid]);
-            if (lane == 0) trace_mark(P, k, row, jt, 0);
-            apply_block_reflectors<true>(b, &sm.u.s.top[0][tid], NT, sm.u.s.v[s], sm.u.s.tau[s]);
-            store_col_smem(sm.u.s.col[s][tid], b);
-            fence_proxy_async_smem();
-            bulk_s2g(colbase + row * TB, sm.u.s.col[s][tid], 128);
-            bulk_commit();
-            bulk_wait_all();
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) { trace_mark(P, k, row, jt, 1); st_release(prog_mine + row, k + 1); }
-        }
+        if (i + 1 < p && ld_relaxed(prog_col + i + 1) >= k) { __threadfence(); issue(i + 1, s ^ 1); have_next = true; }
+        mbar_wait_wd(&pfull[s], (phbits >> s) & 1, wd); phbits ^= 1u << s;
+        float b[TB];
+        load_col_sw(b, pin0 + s * TB * TB, lane);
+        if (lane == 0) trace_mark(P, k, i, k, 0);
+        float ti = tsqrt_warp(b, Rs, xs, lane, publish);         // publishes the previous tile on the way
+        if (lane == 0) trace_mark(P, k, i, k, 1);
+        publish();
+        tauc[i * TB + lane] = ti;
+        store_tile(i, b);
         have_cur = have_next;
     }
-    // tile row k is final for this step: write it back and publish
-    if (active) {
-        float *stg = sm.u.s.col[nrows & 1][tid];
-        float b[TB];
+    publish();
+    // ---- final diagonal tile: R from the chain above the diagonal, GEQRT reflectors below
+    float f[TB];
 #pragma unroll
-        for (int r = 0; r < TB; ++r) b[r] = sm.u.s.top[r][tid];
-        store_col_smem(stg, b);
-        fence_proxy_async_smem();
-        bulk_s2g(colbase + k * TB, stg, 128);
-        bulk_commit();
-        bulk_wait_all();
-        __threadfence();
+    for (int r = 0; r < TB; ++r) f[r] = Rs[r * 33 + lane];
+    store_col_sw(pout, lane, f);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) { tma_store_2d(mapA, k * TB, k * TB, pout); bulk_commit(); bulk_wait_all(); }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------ S(k,g): the sweep engine
+template <int NC>
+struct SweepCtx {
+    __device__ __forceinline__ float *tile(int s, int t) const
+    {
+        return reinterpret_cast<float *>(g_smem + s * Cfg<NC>::STAGE_BYTES + t * TILE_BYTES);
+    }
+    __device__ __forceinline__ float *vtile(int s) const { return tile(s, Cfg<NC>::G); }
+    __device__ __forceinline__ float *tau(int s) const { return tile(s, Cfg<NC>::G + 1); }
+    __device__ __forceinline__ float *top() const { return reinterpret_cast<float *>(g_smem + Cfg<NC>::OFF_TOP); }
+    __device__ __forceinline__ uint64_t *bar(int which, int s) const
+    {
+        return reinterpret_cast<uint64_t *>(g_smem + Cfg<NC>::OFF_BAR) + which * Cfg<NC>::NS + s;
+    }
+    __device__ __forceinline__ uint64_t *full(int s) const { return bar(0, s); }
+    __device__ __forceinline__ uint64_t *computed(int s) const { return bar(1, s); }
+    __device__ __forceinline__ uint64_t *empty(int s) const { return bar(2, s); }
+};
+
+template <int NC>
+__device__ void sweep_loader(const Params &P, const CUtensorMap *mapA, const CUtensorMap *mapV, int k, int g,
+                             const SweepCtx<NC> &cx, Ring &ring, const Watch &wd)
+{
+    using C = Cfg<NC>;
+    const int lane = threadIdx.x & 31;
+    const int p = P.p, nrows = p - k;
+    const int jt = g * C::G + lane;                              // lanes 0..G-1: one tile column each
+    const bool active = lane < C::G && jt > k && jt < P.q;
+    const unsigned amask = __ballot_sync(FULL, active);
+    const uint32_t bytes = __popc(amask) * TILE_BYTES + TILE_BYTES + 128;
+    const int *flag = active ? P.prog + (size_t)jt * p : (lane == C::G ? P.prog + (size_t)k * p : nullptr);
+    const int target = active ? k : k + 1;
+
+    for (int idx = 0; idx <= nrows; ++idx) {
+        const int s = ring.stage;
+        mbar_wait_wd(cx.empty(s), ring.phase ^ 1, wd);
+        if (idx < nrows) {
+            const int row = k + idx;
+            unsigned spins = 0;
+            for (;;) {
+                bool ok = flag ? ld_relaxed(flag + row) >= target : true;
+                if (__all_sync(FULL, ok)) break;
+                __nanosleep(64);
+                wd.check(spins);
+            }
+            __threadfence();
+            fence_proxy_async();
+            if (lane == 0) mbar_arrive_expect_tx(cx.full(s), bytes);
+            __syncwarp();
+            if (active) tma_load_2d(cx.tile(s, lane), mapA, row * TB, jt * TB, cx.full(s));
+            if (lane == C::G) tma_load_2d(cx.vtile(s), mapV, row * TB, k * TB, cx.full(s));
+            if (lane == C::G + 1) bulk_g2s(cx.tau(s), P.tauc + ((size_t)k * p + row) * TB, 128, cx.full(s));
+        } else if (lane == 0) {
+            mbar_arrive(cx.full(s));                            // write-back round: nothing to load
+        }
+        ring.advance<C::NS>();
+    }
+}
+
+template <int NC>
+__device__ void sweep_storer(const Params &P, const CUtensorMap *mapA, int k, int g, const SweepCtx<NC> &cx,
+                             Ring &ring, const Watch &wd)
+{
+    using C = Cfg<NC>;
+    const int lane = threadIdx.x & 31;
+    const int p = P.p, nrows = p - k;
+    const int jt = g * C::G + lane;
+    const bool active = lane < C::G && jt > k && jt < P.q;
+
+    for (int idx = 0; idx <= nrows; ++idx) {
+        const int s = ring.stage;
+        mbar_wait_wd(cx.computed(s), ring.phase, wd);
+        if (idx > 0) {
+            const int row = idx < nrows ? k + idx : k;           // last round writes the resident tile row k
+            if (active) {
+                tma_store_2d(mapA, row * TB, jt * TB, cx.tile(s, lane));
+                bulk_commit();
+                bulk_wait_all();
+                __threadfence();
+                if (idx < nrows) trace_mark(P, k, row, jt, 1);
+                st_release(P.prog + (size_t)jt * p + row, k + 1);
+            }
+        }
         __syncwarp();
-        if (lane == 0) { trace_mark(P, k, k, jt, 1); st_release(prog_mine + k, k + 1); }
+        if (lane == 0) mbar_arrive(cx.empty(s));
+        ring.advance<C::NS>();
     }
 }
 
-// ticket -> macro task.  Keep in lock-step with b200qr_sched_device_order() (sched_host.cpp).
-__device__ __forceinline__ void decode_ticket(const Params &P, int t, int &is_panel, int &k, int &g)
+template <int NC>
+__device__ void sweep_consumer(const Params &P, int k, int g, const SweepCtx<NC> &cx, Ring &ring, const Watch &wd)
 {
-    if (t == 0) { is_panel = 1; k = 0; g = 0; return; }
-    int lo = 0, hi = P.K - 1;                    // largest step with step_start[step] <= t
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (P.step_start[mid] <= t) lo = mid; else hi = mid - 1;
+    using C = Cfg<NC>;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nrows = P.p - k;
+    constexpr int TOPW = C::G * TB;                              // floats per row of the resident tile row
+    float *top = cx.top() + w * TB + lane;                       // column n of this thread: + n*CW*TB
+    bool act[NC];
+    int jts[NC];
+#pragma unroll
+    for (int n = 0; n < NC; ++n) {
+        jts[n] = g * C::G + n * CW + w;
+        act[n] = jts[n] > k && jts[n] < P.q;
     }
-    int r = t - P.step_start[lo];
-    int next_panel = (lo + 1 < P.K) ? 1 : 0;
-    int g0 = (lo + 1) / G;
-    if (r == 0) { is_panel = 0; k = lo; g = g0; }
-    else if (r == 1 && next_panel) { is_panel = 1; k = lo + 1; g = 0; }
-    else { is_panel = 0; k = lo; g = g0 + r - next_panel; }
+
+    for (int idx = 0; idx <= nrows; ++idx) {
+        const int s = ring.stage;
+        mbar_wait_wd(cx.full(s), ring.phase, wd);
+        const float *vs = cx.vtile(s), *ts = cx.tau(s);
+        if (idx < nrows) {
+            const int row = k + idx;
+            float b[2][TB];                                     // b[1] unused when NC == 1
+#pragma unroll
+            for (int n = 0; n < NC; ++n)
+                if (act[n]) {
+                    load_col_sw(b[n], cx.tile(s, n * CW + w), lane);
+                    if (lane == 0) trace_mark(P, k, row, jts[n], 0);
+                }
+            float *t0 = top, *t1 = top + (NC - 1) * CW * TB;
+            if (NC == 2 && act[0] && act[NC - 1]) {
+                if (idx == 0) apply_reflectors_nc<2, false>(b[0], b[1], t0, t1, TOPW, vs, ts);
+                else apply_reflectors_nc<2, true>(b[0], b[1], t0, t1, TOPW, vs, ts);
+            } else if (act[0]) {
+                if (idx == 0) apply_reflectors_nc<1, false>(b[0], b[0], t0, t0, TOPW, vs, ts);
+                else apply_reflectors_nc<1, true>(b[0], b[0], t0, t0, TOPW, vs, ts);
+            } else if (NC == 2 && act[NC - 1]) {
+                if (idx == 0) apply_reflectors_nc<1, false>(b[1], b[1], t1, t1, TOPW, vs, ts);
+                else apply_reflectors_nc<1, true>(b[1], b[1], t1, t1, TOPW, vs, ts);
+            }
+#pragma unroll
+            for (int n = 0; n < NC; ++n)
+                if (act[n]) {
+                    if (idx == 0) {
+#pragma unroll
+                        for (int r = 0; r < TB; ++r) top[r * TOPW + n * CW * TB] = b[n][r];
+                        if (lane == 0) trace_mark(P, k, k, jts[n], 1);
+                    } else {
+                        store_col_sw(cx.tile(s, n * CW + w), lane, b[n]);
+                    }
+                }
+        } else {
+            // write-back round: the resident tile row k goes out through stage s
+#pragma unroll
+            for (int n = 0; n < NC; ++n)
+                if (act[n]) {
+                    float x[TB];
+#pragma unroll
+                    for (int r = 0; r < TB; ++r) x[r] = top[r * TOPW + n * CW * TB];
+                    store_col_sw(cx.tile(s, n * CW + w), lane, x);
+                }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(cx.computed(s));
+        ring.advance<C::NS>();
+    }
 }
 
-__global__ void __launch_bounds__(NT, 3) tiledqr_persistent(const Params P)
+template <int NC>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tiledqr_persistent(const Params P, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapV)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
-    __shared__ int s_task[3];
-    const unsigned long long t0 = gtimer();
+    using C = Cfg<NC>;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(g_smem + C::OFF_BAR);
+    uint64_t *full = bars, *computed = bars + C::NS, *empty = bars + 2 * C::NS, *pfull = bars + 3 * C::NS;
+    int *s_task = reinterpret_cast<int *>(bars + 3 * C::NS + 2 * NPW);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const Watch wd{gtimer(), P.watchdog_ns};
+    const bool split = P.npanel_ctas > 0;
+    const bool panel_cta = !split || (int)blockIdx.x < P.npanel_ctas;
+    const bool sweep_cta = !split || (int)blockIdx.x >= P.npanel_ctas;
 
     if (threadIdx.x == 0) {
-        mbar_init(&sm.sfull[0], NT); mbar_init(&sm.sfull[1], NT);
-        mbar_init(&sm.pfull[0], 32); mbar_init(&sm.pfull[1], 32);
+        for (int s = 0; s < C::NS; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&computed[s], CW * 32);
+            mbar_init(&empty[s], 1);
+        }
+        for (int i = 0; i < 2 * NPW; ++i) mbar_init(&pfull[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapV);
     }
-    uint32_t ph_s[2] = {0, 0}, ph_p[2] = {0, 0};
+    __syncthreads();
 
+    if (warp >= W_PANEL) {
+        if (!panel_cta) return;
+        uint32_t phbits = 0;
+        for (;;) {
+            int t = 0;
+            if (lane == 0) t = atomicAdd(&P.ctr[2], 1);
+            t = __shfl_sync(FULL, t, 0);
+            if (t >= P.K) break;
+            run_panel<NC>(P, &mapA, t, warp - W_PANEL, phbits, wd);
+        }
+        return;
+    }
+    if (!sweep_cta) return;
+
+    SweepCtx<NC> cx;
+    Ring ring;
     for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
+        named_bar_sync(1, SWEEP_THREADS);                        // everyone is done with s_task
+        if (warp == W_LOADER && lane == 0) {
             int t = atomicAdd(&P.ctr[0], 1);
-            int is_panel = -1, k = 0, g = 0;
-            if (t < P.ntickets) decode_ticket(P, t, is_panel, k, g);
-            s_task[0] = is_panel; s_task[1] = k; s_task[2] = g;
+            int2 kg = t < P.nsweeps ? P.sweep_tab[t] : make_int2(-1, 0);
+            s_task[0] = kg.x; s_task[1] = kg.y;
         }
-        __syncthreads();
-        const int is_panel = s_task[0], k = s_task[1], g = s_task[2];
-        if (is_panel < 0) break;
-        if (is_panel) {
-            if (threadIdx.x < 32) run_panel(P, k, sm, ph_p, t0);
-        } else {
-            run_sweep(P, k, g, sm, ph_s, t0);
-        }
+        named_bar_sync(1, SWEEP_THREADS);
+        const int k = s_task[0], g = s_task[1];
+        if (k < 0) break;
+        if (warp == W_LOADER) sweep_loader<NC>(P, &mapA, &mapV, k, g, cx, ring, wd);
+        else if (warp == W_STORER) sweep_storer<NC>(P, &mapA, k, g, cx, ring, wd);
+        else sweep_consumer<NC>(P, k, g, cx, ring, wd);
     }
 }
 
@@ -296,6 +443,7 @@ __global__ void __launch_bounds__(NT, 3) tiledqr_persistent(const Params P)
 __device__ void tile_task_device(int type, int l, int m, int k, float *mat, float *taumat, int ldm,
                                  float *Rs, float *vs, float *ts, float *top)
 {
+    float *xs = vs;                       // panel tasks do not use vs: reuse it as broadcast scratch
     const int lane = threadIdx.x & 31;
     auto tile = [&](float *base, int I, int J) { return base + (size_t)(J * TB + lane) * ldm + I * TB; };
     auto tauv = [&](int I, int J) { return taumat + (size_t)(J * TB) * ldm + I * TB; };
@@ -303,7 +451,7 @@ __device__ void tile_task_device(int type, int l, int m, int k, float *mat, floa
     switch (type) {
     case B200QR_QRS: {
         load_col_gmem(x, tile(mat, k, k));
-        float t = geqrt_warp(x, lane);
+        float t = geqrt_warp(x, xs, lane);
         store_col_gmem(tile(mat, k, k), x);
         tauv(k, k)[lane] = t;
         break;
@@ -314,7 +462,7 @@ __device__ void tile_task_device(int type, int l, int m, int k, float *mat, floa
         for (int r = 0; r < TB; ++r) Rs[r * 33 + lane] = x[r];
         __syncwarp();
         load_col_gmem(x, tile(mat, l, k));
-        float t = tsqrt_warp(x, Rs, lane);
+        float t = tsqrt_warp(x, Rs, xs, lane);
         store_col_gmem(tile(mat, l, k), x);
         float *rcol = tile(mat, k, k);
 #pragma unroll
@@ -440,17 +588,54 @@ static thread_local int g_last_cuda = 0;
 struct b200qr_plan_s {
     int m, n, p, q, K;
     int grid;
-    int ntickets;
+    int nc;                 // matrix columns per consumer thread (1 or 2): kernel variant
+    int npanel_ctas;        // role split (0 = every CTA runs both roles)
+    int nsweeps;            // sweep tickets; panel tickets = K
     long tile_tasks;
     int trace;
-    int *d_prog = nullptr, *d_ctr = nullptr, *d_step_start = nullptr, *d_trace = nullptr;
+    int *d_prog = nullptr, *d_ctr = nullptr, *d_trace = nullptr;
+    int2 *d_sweep_tab = nullptr;
     long long *d_trace_off = nullptr;
     float *d_tauc = nullptr;
     std::vector<long long> trace_off;
     unsigned long long watchdog_ns;
 };
 
-static size_t smem_bytes() { return sizeof(Smem); }
+typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda at link time)
+static tmap_encode_fn tmap_encoder()
+{
+    static tmap_encode_fn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (tmap_encode_fn)ptr;
+    }
+    return fn;
+}
+
+// 2-D map over the column-major matrix: dim0 = rows (contiguous), dim1 = columns (ldm apart);
+// box = one 32x32 tile.
+static int make_tile_map(CUtensorMap *map, float *dA, int m, int n, int ldm, bool swizzle)
+{
+    tmap_encode_fn enc = tmap_encoder();
+    if (!enc) return B200QR_ECUDA;
+    cuuint64_t dims[2] = {(cuuint64_t)m, (cuuint64_t)n};
+    cuuint64_t strides[1] = {(cuuint64_t)ldm * sizeof(float)};
+    cuuint32_t box[2] = {TB, TB}, estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dA, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? B200QR_OK : B200QR_ECUDA;
+}
+
+static const void *kernel_of(int nc) { return nc == 2 ? (const void *)tiledqr_persistent<2> : (const void *)tiledqr_persistent<1>; }
+static int smem_of(int nc) { return nc == 2 ? Cfg<2>::SMEM_BYTES : Cfg<1>::SMEM_BYTES; }
 
 extern "C" {
 
@@ -488,40 +673,62 @@ int b200qr_plan_create(b200qr_plan_t *out, int m, int n, const b200qr_opts *opts
     const char *wd = getenv("QRB200_WATCHDOG_MS");
     pl->watchdog_ns = (unsigned long long)(wd ? atol(wd) : 60000) * 1000000ull;
 
-    // step table of the ticket order (see decode_ticket)
     const int p = pl->p, q = pl->q, K = pl->K;
-    std::vector<int> start(K + 1);
     pl->trace_off.resize(K);
-    int t = 1;
     long tiles = 0;
-    const int GB = (q + G - 1) / G;
-    for (int k = 0; k < K; ++k) {
-        start[k] = t;
-        if (k + 1 < q) t += GB - (k + 1) / G;
-        if (k + 1 < K) t += 1;
-        pl->trace_off[k] = tiles;
-        tiles += (long)(p - k) * (q - k);
-    }
-    start[K] = t;
-    pl->ntickets = t;
+    for (int k = 0; k < K; ++k) { pl->trace_off[k] = tiles; tiles += (long)(p - k) * (q - k); }
     pl->tile_tasks = tiles;
 
-    int dev = 0, sms = 0, occ = 0;
+    int dev = 0, sms = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    CK(cudaFuncSetAttribute(tiledqr_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tiledqr_persistent, NT, smem_bytes()));
+    for (int nc = 1; nc <= 2; ++nc)
+        CK(cudaFuncSetAttribute(kernel_of(nc), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(nc)));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel_of(2), NTHREADS, smem_of(2)));
     if (occ < 1) { delete pl; return B200QR_EINVAL; }
-    int grid = occ * sms;
+    int grid = occ * sms;                          // every CTA must be co-resident (cooperative launch)
     if (opts && opts->grid_ctas > 0 && opts->grid_ctas < grid) grid = opts->grid_ctas;
-    if (grid > pl->ntickets) grid = pl->ntickets;
+
+    // Kernel variant and roles.  Large grids split the roles: a few CTAs run only TSQRT chains
+    // (two panel warps each, undisturbed by the FFMA-bound consumers), the rest only sweeps with
+    // 2 matrix columns per consumer thread (16 tile columns per sweep).  The number of panel
+    // warps sets how many panel chains advance at once: about (chain work) / (sweep work per
+    // warp-time), which is ~2800 / q panel chains on a B200.  Small grids (tests, tiny
+    // matrices) run both roles in every CTA with the 1-column variant.
+    pl->nc = 1; pl->npanel_ctas = 0;
+    if (grid >= 16 && q >= 32) {
+        pl->nc = 2;
+        int want = (2800 / q + 2 + NPW - 1) / NPW;
+        if (want < 2) want = 2;
+        if (want > grid / 4) want = grid / 4;
+        pl->npanel_ctas = want;
+    }
+    if (const char *e = getenv("QRB200_NP")) {
+        int v = atoi(e);
+        if (v > 0 && v < grid && grid >= 2) { pl->npanel_ctas = v; } else if (v == 0) { pl->npanel_ctas = 0; pl->nc = 1; }
+    }
+    if (const char *e = getenv("QRB200_NC")) { int v = atoi(e); if (v == 1 || (v == 2 && pl->npanel_ctas > 0)) pl->nc = v; }
+    const int G = CW * pl->nc;
+
+    // sweep tickets in skewed order (sched_host.cpp)
+    long cap = 0;
+    for (int k = 0; k < K; ++k) if (k + 1 < q) cap += (q + G - 1) / G - (k + 1) / G;
+    std::vector<int> tab(2 * (size_t)(cap > 0 ? cap : 1));
+    long ns = b200qr_sched_sweep_order(p, q, G, tab.data(), cap);
+    if (ns != cap) { delete pl; return B200QR_EINVAL; }
+    pl->nsweeps = (int)ns;
+    const int useful = (pl->nsweeps > K ? pl->nsweeps : K) + pl->npanel_ctas;
+    if (grid > useful) grid = useful;
+    if (pl->npanel_ctas >= grid) pl->npanel_ctas = grid > 1 ? grid / 2 : 0;
+    if (pl->npanel_ctas == 0) pl->nc = 1;
     pl->grid = grid;
 
     CK(cudaMalloc(&pl->d_prog, sizeof(int) * (size_t)p * q));
     CK(cudaMalloc(&pl->d_ctr, sizeof(int) * 64));
-    CK(cudaMalloc(&pl->d_step_start, sizeof(int) * (K + 1)));
+    CK(cudaMalloc(&pl->d_sweep_tab, sizeof(int2) * (size_t)(ns > 0 ? ns : 1)));
+    if (ns > 0) CK(cudaMemcpy(pl->d_sweep_tab, tab.data(), sizeof(int2) * (size_t)ns, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&pl->d_tauc, sizeof(float) * (size_t)K * p * TB));
-    CK(cudaMemcpy(pl->d_step_start, start.data(), sizeof(int) * (K + 1), cudaMemcpyHostToDevice));
     CK(cudaMemset(pl->d_tauc, 0, sizeof(float) * (size_t)K * p * TB));
     if (pl->trace) {
         CK(cudaMalloc(&pl->d_trace, sizeof(int) * 2 * (size_t)tiles));
@@ -535,7 +742,7 @@ int b200qr_plan_create(b200qr_plan_t *out, int m, int n, const b200qr_opts *opts
 int b200qr_plan_destroy(b200qr_plan_t pl)
 {
     if (!pl) return B200QR_EINVAL;
-    cudaFree(pl->d_prog); cudaFree(pl->d_ctr); cudaFree(pl->d_step_start); cudaFree(pl->d_tauc);
+    cudaFree(pl->d_prog); cudaFree(pl->d_ctr); cudaFree(pl->d_sweep_tab); cudaFree(pl->d_tauc);
     cudaFree(pl->d_trace); cudaFree(pl->d_trace_off);
     delete pl;
     return B200QR_OK;
@@ -543,7 +750,7 @@ int b200qr_plan_destroy(b200qr_plan_t pl)
 
 int b200qr_plan_grid(b200qr_plan_t pl) { return pl ? pl->grid : B200QR_EINVAL; }
 long b200qr_plan_tile_tasks(b200qr_plan_t pl) { return pl ? pl->tile_tasks : B200QR_EINVAL; }
-long b200qr_plan_macro_tasks(b200qr_plan_t pl) { return pl ? pl->ntickets : B200QR_EINVAL; }
+long b200qr_plan_macro_tasks(b200qr_plan_t pl) { return pl ? (long)pl->nsweeps + pl->K : B200QR_EINVAL; }
 const float *b200qr_plan_tau_device(b200qr_plan_t pl) { return pl ? pl->d_tauc : nullptr; }
 
 int b200qr_factor_device(b200qr_plan_t pl, float *dA, int ldm, void *stream_)
@@ -556,11 +763,15 @@ int b200qr_factor_device(b200qr_plan_t pl, float *dA, int ldm, void *stream_)
     Params P;
     P.A = dA; P.ldm = ldm; P.p = pl->p; P.q = pl->q; P.K = pl->K;
     P.tauc = pl->d_tauc; P.prog = pl->d_prog; P.ctr = pl->d_ctr;
-    P.step_start = pl->d_step_start; P.ntickets = pl->ntickets;
-    P.trace = pl->trace ? pl->d_trace : nullptr; P.trace_off = pl->d_trace_off;
+    P.sweep_tab = pl->d_sweep_tab; P.nsweeps = pl->nsweeps; P.npanel_ctas = pl->npanel_ctas;
+    P.trace = pl->trace ? pl->d_trace : nullptr; P.trace_off = pl->d_trace_off; P.trace_mode = pl->trace;
     P.watchdog_ns = pl->watchdog_ns;
-    void *args[] = {&P};
-    CK(cudaLaunchCooperativeKernel((void *)tiledqr_persistent, dim3(pl->grid), dim3(NT), args, smem_bytes(), stream));
+    CUtensorMap mapA, mapV;                        // swizzled (thread-per-column tiles) / dense (reflector tiles)
+    int rc = make_tile_map(&mapA, dA, pl->m, pl->n, ldm, true);
+    if (rc == B200QR_OK) rc = make_tile_map(&mapV, dA, pl->m, pl->n, ldm, false);
+    if (rc != B200QR_OK) return rc;
+    void *args[] = {&P, &mapA, &mapV};
+    CK(cudaLaunchCooperativeKernel(kernel_of(pl->nc), dim3(pl->grid), dim3(NTHREADS), args, smem_of(pl->nc), stream));
     return B200QR_OK;
 }
 

@@ -123,14 +123,46 @@ int b200qr_sched_predecessors(const b200qr_task *t, b200qr_task pred[3])
     return n;
 }
 
-// Ticket order of the persistent kernel (see DESIGN.md "scheduler"): macro tasks
-//   P(k)   = QRS(k,k) followed by the QRD chain down tile column k,
-//   S(k,g) = for each tile column j of column group g: SAPP(k,j) then the DAPP chain,
-// issued as P(0), then for every step k: S(k,g0), P(k+1), S(k,g0+1), S(k,g0+2), ...
-// Must stay in lock-step with decode_ticket() in qr_persistent.cu (tests compare both).
+// Sweep ticket order of the persistent kernel.  A sweep S(k,g) = UNMQR(k,j) + the TSMQR chain
+// (i,j), i>k, for the tile columns j of group g (G columns per group).  Tickets are sorted by
+//     key(k,g) = k + G*g      (ties: smaller k first)
+// i.e. a group that is d groups to the right of the diagonal group of step k is handed out
+// about d*G steps later than the diagonal group of the same step.  By then the panel chain
+// P(k) has a long head start, so only the diagonal-group sweeps run in lock-step with a panel;
+// everything else runs at full speed.  For a fixed group the key grows with k, and the panel
+// P(k) only needs S(k-1, diagonal group), whose key is smaller than that of every S(k, .):
+// the order is a topological order of the macro-task DAG (needed for deadlock freedom).
+// out2 receives (k, g) pairs; returns the number of sweeps.
+long b200qr_sched_sweep_order(int M, int N, int G, int *out2, long cap)
+{
+    if (M <= 0 || N <= 0 || G <= 0) return -1;
+    const int K = M < N ? M : N;
+    const int GB = (N + G - 1) / G;
+    // counting sort on key in [0, K + G*GB]
+    std::vector<long> count((size_t)K + (size_t)G * GB + 2, 0);
+    long n = 0;
+    for (int k = 0; k < K; ++k) {
+        if (k + 1 >= N) continue;
+        for (int g = (k + 1) / G; g < GB; ++g) { ++count[(size_t)k + (size_t)G * g + 1]; ++n; }
+    }
+    for (size_t i = 1; i < count.size(); ++i) count[i] += count[i - 1];
+    for (int k = 0; k < K; ++k) {                       // k ascending => ties keep smaller k first
+        if (k + 1 >= N) continue;
+        for (int g = (k + 1) / G; g < GB; ++g) {
+            long pos = count[(size_t)k + (size_t)G * g]++;
+            if (pos < cap) { out2[2 * pos] = k; out2[2 * pos + 1] = g; }
+        }
+    }
+    return n;
+}
+
+// One serial order that is consistent with both ticket streams of the persistent kernel (panel
+// tickets P(0), P(1), ...; sweep tickets as above), expanded to tile tasks (n x 4 ints: type,l,m,k):
+// each panel is emitted just before the first sweep that needs it.  Tests check that this is a
+// topological order of the tile DAG.
 long b200qr_sched_device_order(int M, int N, int *out4, long cap)
 {
-    const int G = 4;                                     // tile columns per sweep task
+    const int G = 16;                                    // tile columns per sweep (2-column variant)
     int K = M < N ? M : N;
     long n = 0;
     auto emit = [&](int type, int l, int m, int k) {
@@ -144,21 +176,20 @@ long b200qr_sched_device_order(int M, int N, int *out4, long cap)
     auto sweep = [&](int k, int g) {
         int j0 = g * G > k + 1 ? g * G : k + 1;
         int j1 = (g + 1) * G < N ? (g + 1) * G : N;
-        // the 4 warps of a sweep CTA advance row by row together
         for (int j = j0; j < j1; ++j) emit(B200QR_SAPP, k, j, k);
-        for (int i = k + 1; i < M; ++i)
+        for (int i = k + 1; i < M; ++i)                  // the consumer warps advance row by row together
             for (int j = j0; j < j1; ++j) emit(B200QR_DAPP, i, j, k);
     };
-    panel(0);
-    int GB = (N + G - 1) / G;
-    for (int k = 0; k < K; ++k) {
-        bool has_cols = k + 1 < N;
-        int g0 = (k + 1) / G;
-        if (has_cols) sweep(k, g0);
-        if (k + 1 < K) panel(k + 1);
-        if (has_cols)
-            for (int g = g0 + 1; g < GB; ++g) sweep(k, g);
+    long ns = b200qr_sched_sweep_order(M, N, G, nullptr, 0);
+    std::vector<int> tab(2 * (size_t)(ns > 0 ? ns : 1));
+    b200qr_sched_sweep_order(M, N, G, tab.data(), ns);
+    int next_panel = 0;
+    for (long t = 0; t < ns; ++t) {
+        int k = tab[2 * t], g = tab[2 * t + 1];
+        while (next_panel <= k) panel(next_panel++);
+        sweep(k, g);
     }
+    while (next_panel < K) panel(next_panel++);
     return n;
 }
 

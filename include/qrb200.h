@@ -53,7 +53,8 @@ typedef struct {
 
 typedef struct {
     int grid_ctas;      /* persistent grid size; 0 = all co-resident CTAs of the device     */
-    int trace;          /* 1 = record a per-tile-task start/finish sequence (DAG tests)      */
+    int trace;          /* 1 = record a per-tile-task start/finish sequence (DAG tests);
+                           2 = record %globaltimer nanoseconds (low 32 bits) instead            */
     int reserved[6];
 } b200qr_opts;
 
@@ -67,6 +68,9 @@ int         b200qr_device_sm_count(void);
 /* Measured FP32 FFMA throughput of the current device in GFLOP/s (register-resident FMA loop
  * on every SM, best of 3 after a warm-up): the roofline denominator of the SIMT kernels.   */
 int         b200qr_measure_fp32_peak(double *gflops, int iters);
+/* SM cycles per tile of the panel kernels run by one warp: cycles4 = {GEQRT alone, TSQRT alone,
+ * GEQRT / TSQRT with eight FFMA-bound warps on the same SM}.  Diagnostic for the scheduler design. */
+int         b200qr_probe_panel(long long *cycles4, int reps);
 
 /* ---- plan: workspace + schedule for one (m, n) shape ----------------------------
  * Replaces the per-call cudaMalloc of task grid / queue / tau in cudaQRTask
@@ -124,8 +128,11 @@ int  b200qr_sched_ready_count(b200qr_sched_t s);
 int  b200qr_sched_dep_count(int type, int k);   /* initial dependency counter of a task */
 /* Predecessors of task t (at most 3); returns how many were written to pred[].      */
 int  b200qr_sched_predecessors(const b200qr_task *t, b200qr_task pred[3]);
-/* The device kernel's macro-task order expanded to tile tasks (n x 4 ints: type,l,m,k):
- * ticket order of the persistent scheduler for an M x N tile grid.                  */
+/* Sweep ticket order of the persistent kernel for an M x N tile grid and G tile columns per
+ * sweep: (k, g) pairs sorted by k + G*g.  Returns the number of sweeps (out2 may be NULL).    */
+long b200qr_sched_sweep_order(int M, int N, int G, int *out2, long cap);
+/* One serial order consistent with both ticket streams of the device scheduler, expanded to
+ * tile tasks (n x 4 ints: type,l,m,k).                                               */
 long b200qr_sched_device_order(int M, int N, int *out4, long cap);
 
 #ifdef __cplusplus

@@ -77,7 +77,7 @@ def test_golden_fixture_128(cuda, qr, golden_small):
         m, n = map(int, key.split("x"))
         out, tau, _, _ = factor_device(qr, cuda, golden_small["in_" + key], m, n)
         assert np.max(np.abs(out - golden_small["out_" + key])) <= 1e-4 * 8
-        assert np.max(np.abs(tau - golden_small["tau_" + key])) <= 1e-5
+        assert np.max(np.abs(tau - golden_small["tau_" + key])) <= 1e-5 * max(1, n // 32)
 
 
 def test_leading_dimension_and_padding_untouched(cuda, qr, po):
