@@ -14,26 +14,40 @@ for _ in range(2):
     torch.cuda.synchronize()
 tr = plan.read_trace().astype(np.int64)
 t0 = tr[:, 4].min()
-st = {tuple(r[:4]): (int(r[4] - t0), int(r[5] - t0)) for r in tr}
 p = n // 32
-print("total span us", (tr[:, 5].max() - t0) / 1e3, "grid", plan.grid, "macro", plan.macro_tasks)
-def chain(k, col, typ_first, typ_rest):
-    out = []
-    for i in range(k, p):
-        ty = typ_first if i == k else typ_rest
-        out.append(st[(ty, i, col, k)])
-    return np.array(out)
-for k in (0, 1, 2, 5, 10, 20, p // 2):
-    if k >= p - 2: continue
-    c = chain(k, k, 0, 2)
-    dur = (c[:, 1] - c[:, 0])
-    pace = np.diff(c[:, 1])
-    print("P(%d): start %.1f us, end %.1f us, tile compute median %.2f us, pace median %.2f us p90 %.2f" % (
-        k, c[0, 0] / 1e3, c[-1, 1] / 1e3, np.median(dur) / 1e3, np.median(pace) / 1e3, np.percentile(pace, 90) / 1e3))
-    for col in (k + 1, min(p - 1, k + 20)):
-        s = chain(k, col, 1, 3)
-        dur = (s[1:, 1] - s[1:, 0]); pace = np.diff(s[1:, 1])
-        if len(pace) == 0: continue
-        lag = s[1:, 0] - c[1:, 1]
-        print("   S col %d: start %.1f end %.1f, row start->publish median %.2f us, pace median %.2f p90 %.2f, lag behind panel finish median %.2f us" % (
-            col, s[0, 0] / 1e3, s[-1, 1] / 1e3, np.median(dur) / 1e3, np.median(pace) / 1e3, np.percentile(pace, 90) / 1e3, np.median(lag) / 1e3))
+span = (tr[:, 5].max() - t0) / 1e3
+print("n", n, "total span us %.1f" % span, "grid", plan.grid, "macro", plan.macro_tasks)
+# index: per step k block of (p-k)*(q-k) records ordered j-major then i (see b200qr_plan_read_trace)
+off = 0
+S = np.zeros((p, p, p, 2), dtype=np.float32) if n <= 2048 else None
+rows = {}
+off = 0
+pan, far, near = [], [], []
+for k in range(p):
+    cnt = (p - k) * (p - k)
+    blk = tr[off:off + cnt].reshape(p - k, p - k, 6)      # [j-k][i-k]
+    off += cnt
+    st = (blk[:, :, 4] - t0) / 1e3
+    fi = (blk[:, :, 5] - t0) / 1e3
+    pan.append((k, st[0, 0], fi[0, -1], np.median(np.diff(fi[0])) if p - k > 2 else 0))
+    if p - k > 40:
+        j1 = 1
+        jf = p - k - 1
+        near.append((k, st[j1, 0], fi[j1, -1], np.median(np.diff(fi[j1, 1:]))))
+        far.append((k, st[jf, 0], fi[jf, -1], np.median(np.diff(fi[jf, 1:]))))
+pan = np.array(pan); near = np.array(near); far = np.array(far)
+for k in sorted(set([0, 1, 2, 8, 16, 32, p // 4, p // 2, 3 * p // 4, p - 2]) & set(range(p))):
+    r = pan[k]
+    line = "P(%3d): start %8.1f end %8.1f pace %.2f us" % (k, r[1], r[2], r[3])
+    m = near[near[:, 0] == k]
+    if len(m):
+        line += " | near sweep: start %8.1f end %8.1f pace %.2f" % tuple(m[0, 1:])
+        f = far[far[:, 0] == k][0]
+        line += " | far sweep: start %8.1f end %8.1f pace %.2f" % tuple(f[1:])
+    print(line)
+# concurrency of panels over time
+ts = np.linspace(0, span, 21)[1:-1]
+conc = [(int(((pan[:, 1] <= t) & (pan[:, 2] >= t)).sum())) for t in ts]
+print("active panels at 5%..95% of the run:", conc)
+print("far-sweep pace median over steps: %.2f us; near-sweep pace median: %.2f us; panel pace median %.2f us" % (
+    np.median(far[:, 3]), np.median(near[:, 3]), np.median(pan[:p - 2, 3])))
