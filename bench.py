@@ -144,83 +144,77 @@ def run_reference(args, rank, world):
 
 
 def run_b200(args, rank, world, local_rank):
-    import numpy as np
     import torch
-    import torch.distributed as dist
-    import gpu_tiled_qr_decomposition_b200 as q
-
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device visible; the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    if world > 1:
+        return run_b200_multi(args, rank, world, local_rank)
+    return run_b200_single(args)
+
+
+def gram_check(torch, d, A0, c0, c1):
+    """|R^T R - A^T A| / |A^T A| restricted to matrix columns [c0, c1): needs only those columns of
+    the factored matrix d (R on/above the diagonal) and of the input A0.  Storage is (n, ld)."""
+    rows = torch.arange(c1, device=d.device)[:, None]
+    cols = torch.arange(c0, c1, device=d.device)[None, :]
+    R = torch.where(rows <= cols, d[c0:c1, :c1].t().double(), torch.zeros((), dtype=torch.float64, device=d.device))
+    Ad = A0[c0:c1].t().double()
+    G2 = Ad.t() @ Ad
+    return (torch.linalg.norm(R.t() @ R - G2) / torch.linalg.norm(G2)).item()
+
+
+def run_b200_single(args):
+    import torch
+    import gpu_tiled_qr_decomposition_b200 as q
     q.build()
     L = q.lib()
     n = args.size
     flops = qr_flops(n, n)
     stream = torch.cuda.current_stream().cuda_stream
 
-    g = torch.Generator(device="cuda").manual_seed(5 + rank)
+    g = torch.Generator(device="cuda").manual_seed(5)
     A0 = torch.rand((n, n), generator=g, device="cuda", dtype=torch.float32) * 2 - 1   # uniform[-1,1)
     d = torch.empty_like(A0)
     plan = q.Plan(n, n)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     for _ in range(args.warmup):
         d.copy_(A0)
         plan.factor(d.data_ptr(), n, stream)
     torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler = ClockSampler(0)
+    sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
+    torch.cuda.synchronize()
     for e0, e1 in evs:
-        d.copy_(A0)                       # restore the input; 256 MiB copy also evicts L2
+        d.copy_(A0)                       # restore the input; the copy also evicts L2
         e0.record()
         plan.factor(d.data_ptr(), n, stream)
         e1.record()
-    barrier()
-    ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = t.item() / args.steps
-    value = world * flops / (ms_step * 1e-3) * 1e-9
-
-    # quick sanity of the timed result (not in the timed region): Gram identity R^T R = A^T A
-    R = torch.triu(d.t()[:2048, :2048].double())
-    Ad = A0.t()[:, :2048].double()
-    gram = (torch.linalg.norm(R.t() @ R - Ad.t() @ Ad) / torch.linalg.norm(Ad.t() @ Ad)).item()
+    torch.cuda.synchronize()
+    ms_step = sum(e0.elapsed_time(e1) for e0, e1 in evs) / args.steps
+    clocks = sampler.stop()
+    value = flops / (ms_step * 1e-3) * 1e-9
+    gram = gram_check(torch, d, A0, 0, min(n, 2048))
 
     # ---- e2e: the legacy host entry point on a pinned host buffer
     os.environ["QRB200_QUIET"] = "1"
     h0 = A0.cpu()
     h = torch.empty((n, n), dtype=torch.float32).pin_memory()
     e2e_steps = max(1, min(args.steps, 3))
-    h.copy_(h0)
-    L.cudaQRTask(C.c_void_p(h.data_ptr()), n, n, n, 128)          # warm-up
+    for _ in range(2):                                            # warm-up (context, pinned pages)
+        h.copy_(h0)
+        L.cudaQRTask(C.c_void_p(h.data_ptr()), n, n, n, 128)
     e2e_s = 0.0
-    barrier()
     for _ in range(e2e_steps):
         h.copy_(h0)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         L.cudaQRTask(C.c_void_p(h.data_ptr()), n, n, n, 128)
         e2e_s += time.perf_counter() - t0
-    barrier()
-    t = torch.tensor([e2e_s / e2e_steps], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = world * flops / t.item() * 1e-9
-    e2e_err = float((h[:64, :64] - d.cpu()[:64, :64]).abs().max()) if world == 1 else 0.0
+    e2e_val = flops / (e2e_s / e2e_steps) * 1e-9
+    e2e_err = float((h[:64, :64] - d.cpu()[:64, :64]).abs().max())
 
-    if rank != 0:
-        return
     peaks, peak_src = measured_peaks()
     fp32 = C.c_double(0)
     q.check(L.b200qr_measure_fp32_peak(C.byref(fp32), 20000))
@@ -232,18 +226,15 @@ def run_b200(args, rank, world, local_rank):
                                "only HBM and bf16-tensor peaks" % peak_src,
                 "frac_of_bf16_tensor_peak": achieved_tf / peaks["bf16_tflops"],
                 "hbm_algorithmic_gbs": 8.0 * n * n / (ms_step * 1e-3) * 1e-9}
-    cpu = None
-    if world == 1 or True:
-        sec, kind, cores = cpu_reference_run(args.cpu_sample, reps=1)
-        cpu = {"value": qr_flops(args.cpu_sample, args.cpu_sample) / sec * 1e-9, "unit": "GFLOP/s", "cores": cores,
-               "kind": kind, "sample": "%dx%d RANDZO matrix, b=32, one run of taskQRP_threads (%.1f s), "
-               "-O3 -march=x86-64-v3, host has %d cpus" % (args.cpu_sample, args.cpu_sample, sec, os.cpu_count())}
-    line = {"metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic uniform[-1,1), torch cuda generator seed 5+rank",
+    sec, kind, cores = cpu_reference_run(args.cpu_sample, reps=1)
+    cpu = {"value": qr_flops(args.cpu_sample, args.cpu_sample) / sec * 1e-9, "unit": "GFLOP/s", "cores": cores,
+           "kind": kind, "sample": "%dx%d RANDZO matrix, b=32, one run of taskQRP_threads (%.1f s), "
+           "-O3 -march=x86-64-v3, host has %d cpus" % (args.cpu_sample, args.cpu_sample, sec, os.cpu_count())}
+    line = {"metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic uniform[-1,1), torch cuda generator seed 5",
             "config": {"workload": "%dx%d square tiled QR, tile size 32 (reference default), flat-tree TS kernels"
-                                   % (n, n),
-                       "parallelism": "1 GPU" if world == 1 else "%d independent replicas (one matrix per GPU)" % world,
+                                   % (n, n), "parallelism": "1 GPU",
                        "l2": "input restored from a pristine %d MiB copy before every timed step (> 126 MB L2)"
                              % (4 * n * n >> 20),
                        "persistent_grid_ctas": plan.grid, "tile_tasks": plan.tile_tasks,
@@ -258,6 +249,141 @@ def run_b200(args, rank, world, local_rank):
     plan.close()
 
 
+def run_b200_multi(args, rank, world, local_rank):
+    """N > 1: one 32768 x 32768 matrix (BASELINE.json configs[4]), tile columns dealt to the ranks
+    1-D block-cyclically; every rank runs the persistent kernel on its own GPU and reads the other
+    ranks' reflector tiles over NVLink from inside it.  Strong scaling: total work is fixed."""
+    import torch
+    import torch.distributed as dist
+    import gpu_tiled_qr_decomposition_b200 as q
+    q.build()
+    L = q.lib()
+    n = args.multi_size
+    flops = qr_flops(n, n)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    rk = q.DistRank(n, n, rank, world)
+    blobs = [None] * world
+    dist.all_gather_object(blobs, rk.export())
+    rk.connect(blobs)
+    g = torch.Generator(device="cuda").manual_seed(5)            # same matrix on every rank
+    A0 = torch.rand((n, n), generator=g, device="cuda", dtype=torch.float32) * 2 - 1
+    own = rk.owned_tile_cols()
+
+    def one_step(timed):
+        rk.upload(A0.data_ptr())                                 # restore (device-to-device, evicts L2)
+        rk.reset(stream)
+        torch.cuda.synchronize()
+        dist.barrier()                                           # every rank has reset its progress words
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rk.factor(stream)
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        return e0.elapsed_time(e1)
+
+    for _ in range(args.warmup):
+        one_step(False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dist.barrier(); torch.cuda.synchronize()
+    ms = sum(one_step(True) for _ in range(args.steps))
+    dist.barrier(); torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    value = flops / (ms_step * 1e-3) * 1e-9
+
+    # check on the rank's first owned block of tile columns (local data only)
+    d = torch.empty_like(A0)
+    rk.download(d.data_ptr())
+    j0 = own[0]
+    j1 = j0
+    while j1 + 1 in own and j1 + 1 - j0 < rk.block:
+        j1 += 1
+    gram = gram_check(torch, d, A0, j0 * 32, (j1 + 1) * 32)
+    t = torch.tensor([gram], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    gram = t.item()
+    del d
+
+    # e2e: owned columns travel host -> device -> host around the factorisation
+    cols = torch.tensor([c for j in own for c in range(j * 32, (j + 1) * 32)], device="cuda")
+    h_in = A0[cols].cpu().pin_memory()
+    h_out = torch.empty_like(h_in).pin_memory()
+    dwork = torch.empty((len(cols), n), device="cuda", dtype=torch.float32)
+    mat = None
+    e2e_s = 0.0
+    e2e_steps = max(1, min(args.steps, 2))
+    full = torch.empty((n, n), device="cuda", dtype=torch.float32)
+    for it in range(e2e_steps + 1):
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dwork.copy_(h_in, non_blocking=True)                     # H2D of the owned columns
+        full[cols] = dwork
+        rk.upload(full.data_ptr())
+        rk.reset(stream)
+        torch.cuda.synchronize()
+        dist.barrier()
+        rk.factor(stream)
+        rk.download(full.data_ptr())
+        h_out.copy_(full[cols], non_blocking=True)               # D2H of the owned columns
+        torch.cuda.synchronize()
+        dist.barrier()
+        if it > 0:
+            e2e_s += time.perf_counter() - t0
+    t = torch.tensor([e2e_s / e2e_steps], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = flops / t.item() * 1e-9
+    del full, dwork
+
+    # the same workload on ONE GPU (rank 0, one step) so the strong-scaling ratio can be read off this line
+    single = None
+    if rank == 0 and not args.no_single_ref:
+        plan = q.Plan(n, n)
+        d = A0.clone()
+        plan.factor(d.data_ptr(), n, stream)
+        torch.cuda.synchronize()
+        d.copy_(A0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); plan.factor(d.data_ptr(), n, stream); e1.record()
+        torch.cuda.synchronize()
+        single = flops / (e0.elapsed_time(e1) * 1e-3) * 1e-9
+        plan.close()
+        del d
+    dist.barrier()
+    if rank != 0:
+        rk.close()
+        return
+    peaks, peak_src = measured_peaks()
+    fp32 = C.c_double(0)
+    q.check(L.b200qr_measure_fp32_peak(C.byref(fp32), 20000))
+    achieved_tf = value * 1e-3
+    roofline = {"bound": "fp32-simt", "achieved": achieved_tf, "peak": fp32.value * 1e-3 * world, "unit": "TFLOP/s",
+                "frac": achieved_tf / (fp32.value * 1e-3 * world), "traffic": None,
+                "kernel": "tiledqr_persistent (one launch per rank per step)",
+                "peak_source": "FFMA microbench on rank 0 x %d GPUs; %s carries only HBM and bf16-tensor peaks"
+                               % (world, peak_src)}
+    line = {"metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic uniform[-1,1), torch cuda generator seed 5",
+            "config": {"workload": "%dx%d square tiled QR, tile size 32, flat-tree TS kernels" % (n, n),
+                       "parallelism": "1-D block-cyclic tile columns (blocks of %d tile columns) over %d GPUs; reflector "
+                                      "tiles read from the owner over NVLink inside the persistent kernel" % (rk.block, world),
+                       "l2": "input restored from a pristine copy before every timed step",
+                       "persistent_grid_ctas_per_rank": rk.grid,
+                       "single_gpu_same_workload_gflops": single},
+            "roofline": roofline, "cpu_baseline": None,
+            "e2e": {"value": e2e_val, "unit": "GFLOP/s", "h2d_bytes_per_step": 4 * n * n, "d2h_bytes_per_step": 4 * n * n,
+                    "api": "b200qr_dist_* with pinned host copies of the owned columns", "steps": e2e_steps},
+            "gpu_launches": args.steps * world, "clocks": clocks, "check": {"gram_rel_err_owned_block_max": gram}}
+    print(json.dumps(line), flush=True)
+    rk.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -267,6 +393,8 @@ def main():
     ap.add_argument("--size", type=int, default=8192)
     ap.add_argument("--cpu-sample", type=int, default=4096, help="CPU baseline sample size (square)")
     ap.add_argument("--ref-size", type=int, default=0)
+    ap.add_argument("--multi-size", type=int, default=32768, help="matrix size of the N > 1 (block-cyclic) workload")
+    ap.add_argument("--no-single-ref", action="store_true", help="N > 1: skip the same-size single-GPU reference step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

@@ -17,14 +17,18 @@ TASK_AVAIL, TASK_NONE, TASK_DONE = 0, 1, 2
 
 # every symbol include/qrb200.h and include/gpucalc_compat.h declare
 EXPORTS = (
-    "b200qr_version", "b200qr_strerror", "b200qr_last_cuda_error", "b200qr_device_sm_count",
+    "b200qr_version", "b200qr_strerror", "b200qr_last_cuda_error", "b200qr_device_sm_count", "b200qr_copy",
     "b200qr_measure_fp32_peak", "b200qr_probe_panel",
     "b200qr_plan_create", "b200qr_plan_destroy", "b200qr_plan_grid", "b200qr_plan_tile_tasks",
     "b200qr_plan_macro_tasks", "b200qr_factor_device", "b200qr_plan_tau_device",
     "b200qr_tau_to_reference", "b200qr_factor_host", "b200qr_plan_read_trace", "b200qr_tile_task",
     "b200qr_sched_init", "b200qr_sched_next", "b200qr_sched_done", "b200qr_sched_free",
     "b200qr_sched_progress", "b200qr_sched_ready_count", "b200qr_sched_dep_count",
-    "b200qr_sched_predecessors", "b200qr_sched_device_order", "b200qr_sched_sweep_order",
+    "b200qr_sched_predecessors", "b200qr_sched_device_order", "b200qr_sched_sweep_order", "b200qr_sched_rank_tickets",
+    "b200qr_dist_create", "b200qr_dist_destroy", "b200qr_dist_handle_bytes", "b200qr_dist_export",
+    "b200qr_dist_connect", "b200qr_dist_matrix", "b200qr_dist_tau_device", "b200qr_dist_block",
+    "b200qr_dist_owner", "b200qr_dist_grid", "b200qr_dist_reset", "b200qr_dist_factor",
+    "b200qr_dist_connect_local", "b200qr_dist_factor_group",
     "cudaQRTask", "cudaQRFull", "testDAPP", "doCUDADAPP",
 )
 
@@ -38,7 +42,7 @@ class Task(C.Structure):
 
 
 class Opts(C.Structure):
-    _fields_ = [("grid_ctas", C.c_int), ("trace", C.c_int), ("reserved", C.c_int * 6)]
+    _fields_ = [("grid_ctas", C.c_int), ("trace", C.c_int), ("share_device", C.c_int), ("reserved", C.c_int * 5)]
 
 
 def build(force=False):
@@ -68,6 +72,7 @@ def lib():
         vp, ip, fp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)
         L.b200qr_strerror.restype = C.c_char_p
         L.b200qr_strerror.argtypes = [C.c_int]
+        L.b200qr_copy.argtypes = [vp, vp, C.c_size_t]
         L.b200qr_measure_fp32_peak.argtypes = [C.POINTER(C.c_double), C.c_int]
         L.b200qr_probe_panel.argtypes = [C.POINTER(C.c_longlong), C.c_int]
         L.b200qr_plan_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(Opts)]
@@ -97,6 +102,24 @@ def lib():
         L.b200qr_sched_device_order.restype = C.c_long
         L.b200qr_sched_sweep_order.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.c_long]
         L.b200qr_sched_sweep_order.restype = C.c_long
+        L.b200qr_sched_rank_tickets.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_long, vp, C.c_long,
+                                                C.POINTER(C.c_long)]
+        L.b200qr_sched_rank_tickets.restype = C.c_long
+        L.b200qr_dist_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Opts)]
+        L.b200qr_dist_destroy.argtypes = [vp]
+        L.b200qr_dist_export.argtypes = [vp, vp]
+        L.b200qr_dist_connect.argtypes = [vp, vp]
+        L.b200qr_dist_matrix.argtypes = [vp]
+        L.b200qr_dist_matrix.restype = vp
+        L.b200qr_dist_tau_device.argtypes = [vp]
+        L.b200qr_dist_tau_device.restype = vp
+        L.b200qr_dist_block.argtypes = [vp]
+        L.b200qr_dist_owner.argtypes = [vp, C.c_int]
+        L.b200qr_dist_grid.argtypes = [vp]
+        L.b200qr_dist_reset.argtypes = [vp, vp]
+        L.b200qr_dist_factor.argtypes = [vp, vp]
+        L.b200qr_dist_connect_local.argtypes = [C.POINTER(vp), C.c_int]
+        L.b200qr_dist_factor_group.argtypes = [C.POINTER(vp), C.c_int, vp]
         L.cudaQRTask.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
         L.cudaQRTask.restype = None
         L.cudaQRFull.argtypes = [vp, C.c_int, C.c_int]
@@ -201,3 +224,89 @@ def device_order(M, N):
     n = lib().b200qr_sched_device_order(M, N, out.ctypes.data_as(C.c_void_p), cap)
     assert n == cap, (n, cap)
     return out
+
+
+class DistRank:
+    """One rank of the 1-D block-cyclic multi-GPU factorisation (b200qr_dist_*)."""
+
+    def __init__(self, m, n, rank, world, share_device=0, grid_ctas=0):
+        self.m, self.n, self.rank, self.world = m, n, rank, world
+        self._h = C.c_void_p()
+        o = Opts()
+        o.grid_ctas, o.share_device = int(grid_ctas), int(share_device)
+        check(lib().b200qr_dist_create(C.byref(self._h), m, n, rank, world, C.byref(o)), "b200qr_dist_create")
+        self.block = lib().b200qr_dist_block(self._h)
+
+    def export(self):
+        buf = C.create_string_buffer(lib().b200qr_dist_handle_bytes())
+        check(lib().b200qr_dist_export(self._h, buf), "b200qr_dist_export")
+        return buf.raw
+
+    def connect(self, blobs):
+        """blobs: the exported handle bytes of all ranks, in rank order."""
+        raw = b"".join(blobs)
+        check(lib().b200qr_dist_connect(self._h, C.c_char_p(raw)), "b200qr_dist_connect")
+
+    @property
+    def matrix_ptr(self):
+        return lib().b200qr_dist_matrix(self._h)
+
+    @property
+    def tau_ptr(self):
+        return lib().b200qr_dist_tau_device(self._h)
+
+    @property
+    def grid(self):
+        return lib().b200qr_dist_grid(self._h)
+
+    def owner(self, tile_col):
+        return (tile_col // self.block) % self.world
+
+    def owned_tile_cols(self):
+        return [j for j in range(self.n // TILE) if self.owner(j) == self.rank]
+
+    def upload(self, src_ptr):
+        """Copy a full m x n float32 matrix (host or device pointer, ld = m) into the rank's matrix."""
+        check(lib().b200qr_copy(C.c_void_p(self.matrix_ptr), C.c_void_p(src_ptr), self.m * self.n * 4), "b200qr_copy")
+
+    def download(self, dst_ptr):
+        check(lib().b200qr_copy(C.c_void_p(dst_ptr), C.c_void_p(self.matrix_ptr), self.m * self.n * 4), "b200qr_copy")
+
+    def download_tau(self, dst_ptr):
+        """Compact tau [(k*p + i)*32 + r], K*p*32 floats."""
+        p, K = self.m // TILE, min(self.m, self.n) // TILE
+        check(lib().b200qr_copy(C.c_void_p(dst_ptr), C.c_void_p(self.tau_ptr), K * p * TILE * 4), "b200qr_copy")
+
+    def reset(self, stream=0):
+        check(lib().b200qr_dist_reset(self._h, C.c_void_p(stream)), "b200qr_dist_reset")
+
+    def factor(self, stream=0):
+        check(lib().b200qr_dist_factor(self._h, C.c_void_p(stream)), "b200qr_dist_factor")
+
+    def close(self):
+        if self._h:
+            lib().b200qr_dist_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+def dist_connect_local(ranks):
+    arr = (C.c_void_p * len(ranks))(*[r._h for r in ranks])
+    check(lib().b200qr_dist_connect_local(arr, len(ranks)), "b200qr_dist_connect_local")
+
+
+def dist_factor_group(ranks, stream=0):
+    arr = (C.c_void_p * len(ranks))(*[r._h for r in ranks])
+    check(lib().b200qr_dist_factor_group(arr, len(ranks), C.c_void_p(stream)), "b200qr_dist_factor_group")
+
+
+def rank_tickets(M, N, G, rank, world):
+    """(sweeps [(k, g)...], panels [k...]) of one rank of the block-cyclic distribution."""
+    import numpy as np
+    L = lib()
+    npan = C.c_long(0)
+    ns = L.b200qr_sched_rank_tickets(M, N, G, rank, world, None, 0, None, 0, C.byref(npan))
+    sw = np.zeros((max(ns, 1), 2), dtype=np.int32)
+    pa = np.zeros(max(npan.value, 1), dtype=np.int32)
+    L.b200qr_sched_rank_tickets(M, N, G, rank, world, sw.ctypes.data_as(C.c_void_p), ns,
+                                pa.ctypes.data_as(C.c_void_p), npan.value, C.byref(npan))
+    return sw[:ns], pa[:npan.value]

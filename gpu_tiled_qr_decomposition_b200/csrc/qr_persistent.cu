@@ -44,7 +44,15 @@ constexpr int NTHREADS = (CW + 2 + NPW) * 32; // + loader, storer, panel warps
 constexpr int SWEEP_THREADS = (CW + 2) * 32;  // threads that share a sweep ticket
 constexpr int W_LOADER = CW, W_STORER = CW + 1, W_PANEL = CW + 2;
 constexpr int TILE_BYTES = TB * TB * 4;
+constexpr int MAXW = 8;                       // ranks (GPUs) a matrix can be spread over
+constexpr int MAXV = 2;                       // ranks one launch can emulate on a single device (tests)
 
+// Multi-GPU: tile columns are dealt to the ranks in groups of G (the sweep width), group g to
+// rank g % world.  A rank runs the panels of its own tile columns and the sweeps of its own
+// groups; the only data it needs from elsewhere are the reflector tiles V(i,k), their tau and
+// the panel progress words of a step whose panel column lives on another rank, and it reads
+// those straight out of the owner's memory over NVLink (TMA / bulk loads and system-scope
+// polls on peer pointers) from inside the same persistent kernel -- no host step, no staging.
 struct Params {
     float *A;
     int ldm, p, q, K;
@@ -53,6 +61,11 @@ struct Params {
     int *ctr;                 // [0] sweep tickets, [1] trace sequence, [2] panel tickets
     const int2 *sweep_tab;    // sweep ticket -> (k, g), in the skewed order of b200qr_sched_sweep_order()
     int nsweeps;
+    const int *panel_tab;     // panel ticket -> k (the steps whose panel column this rank owns)
+    int npanels;
+    int rank, world;
+    const int *peer_prog[MAXW];     // progress words of every rank ([rank] = prog)
+    const float *peer_tauc[MAXW];   // compact tau of every rank ([rank] = tauc)
     int npanel_ctas;          // > 0: role split -- CTAs [0, npanel_ctas) run only panel warps, the rest only sweeps;
                               // 0: every CTA runs both (small grids; NC = 1 only)
     int trace_mode;           // 1 = global sequence numbers, 2 = low 32 bits of %globaltimer (ns)
@@ -81,6 +94,17 @@ struct Cfg {
 // of the CTA's window: 1024-byte aligned as the 128B-swizzled TMA tiles need).  Every access goes
 // through this symbol so the compiler keeps the shared address space (LDS/STS, not generic LD/ST).
 extern __shared__ __align__(1024) unsigned char g_smem[];
+
+struct RankCtx {
+    Params P;
+    CUtensorMap mapA;               // this rank's matrix, 128B-swizzled tiles (thread-per-column access)
+    CUtensorMap mapV[MAXW];         // every rank's matrix, dense tiles (reflector tiles, broadcast reads)
+};
+struct alignas(64) KernelArgs {
+    int nvirt;                      // ranks emulated by this launch: CTA b works for rank slot b % nvirt
+    int pad[15];
+    RankCtx rc[MAXV];
+};
 
 struct Ring {
     int stage = 0;
@@ -119,6 +143,11 @@ __device__ __forceinline__ void wait_flag(const int *p, int target, const Watch 
     unsigned spins = 0;
     while (ld_relaxed(p) < target) { __nanosleep(32); w.check(spins); }
     __threadfence();
+}
+// acquire / release fences at the scope the run needs (system scope once peers read our memory)
+__device__ __forceinline__ void fence_acq_rel(bool multi)
+{
+    if (multi) __threadfence_system(); else __threadfence();
 }
 
 __device__ __forceinline__ long long trace_slot(const Params &P, int k, int i, int j)
@@ -160,8 +189,8 @@ __device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int p
         if (pending >= 0) {
             if (lane == 0) {
                 bulk_wait_all();
-                __threadfence();
-                st_release(prog_col + pending, k + 1);
+                if (P.world > 1) { __threadfence_system(); st_release_sys(prog_col + pending, k + 1); }
+                else { __threadfence(); st_release(prog_col + pending, k + 1); }
             }
             pending = -1;
         }
@@ -242,7 +271,7 @@ struct SweepCtx {
 };
 
 template <int NC>
-__device__ void sweep_loader(const Params &P, const CUtensorMap *mapA, const CUtensorMap *mapV, int k, int g,
+__device__ void sweep_loader(const Params &P, const CUtensorMap *mapA, const CUtensorMap *mapVs, int k, int g,
                              const SweepCtx<NC> &cx, Ring &ring, const Watch &wd)
 {
     using C = Cfg<NC>;
@@ -252,7 +281,12 @@ __device__ void sweep_loader(const Params &P, const CUtensorMap *mapA, const CUt
     const bool active = lane < C::G && jt > k && jt < P.q;
     const unsigned amask = __ballot_sync(FULL, active);
     const uint32_t bytes = __popc(amask) * TILE_BYTES + TILE_BYTES + 128;
-    const int *flag = active ? P.prog + (size_t)jt * p : (lane == C::G ? P.prog + (size_t)k * p : nullptr);
+    const int owner = (k / C::G) % P.world;                      // rank holding the panel column of step k
+    const bool remote = owner != P.rank;
+    const CUtensorMap *mapV = mapVs + owner;
+    const float *tau_src = P.peer_tauc[owner] + (size_t)k * p * TB;
+    const int *flag = active ? P.prog + (size_t)jt * p : (lane == C::G ? P.peer_prog[owner] + (size_t)k * p : nullptr);
+    const bool flag_remote = remote && lane == C::G;
     const int target = active ? k : k + 1;
 
     for (int idx = 0; idx <= nrows; ++idx) {
@@ -262,18 +296,18 @@ __device__ void sweep_loader(const Params &P, const CUtensorMap *mapA, const CUt
             const int row = k + idx;
             unsigned spins = 0;
             for (;;) {
-                bool ok = flag ? ld_relaxed(flag + row) >= target : true;
+                bool ok = flag ? (flag_remote ? ld_relaxed_sys(flag + row) : ld_relaxed(flag + row)) >= target : true;
                 if (__all_sync(FULL, ok)) break;
                 __nanosleep(64);
                 wd.check(spins);
             }
-            __threadfence();
+            fence_acq_rel(remote);
             fence_proxy_async();
             if (lane == 0) mbar_arrive_expect_tx(cx.full(s), bytes);
             __syncwarp();
             if (active) tma_load_2d(cx.tile(s, lane), mapA, row * TB, jt * TB, cx.full(s));
             if (lane == C::G) tma_load_2d(cx.vtile(s), mapV, row * TB, k * TB, cx.full(s));
-            if (lane == C::G + 1) bulk_g2s(cx.tau(s), P.tauc + ((size_t)k * p + row) * TB, 128, cx.full(s));
+            if (lane == C::G + 1) bulk_g2s(cx.tau(s), tau_src + (size_t)row * TB, 128, cx.full(s));
         } else if (lane == 0) {
             mbar_arrive(cx.full(s));                            // write-back round: nothing to load
         }
@@ -381,17 +415,22 @@ __device__ void sweep_consumer(const Params &P, int k, int g, const SweepCtx<NC>
 
 template <int NC>
 __global__ void __launch_bounds__(NTHREADS, 1)
-tiledqr_persistent(const Params P, const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapV)
+tiledqr_persistent(const __grid_constant__ KernelArgs KA)
 {
     using C = Cfg<NC>;
+    const int vr = KA.nvirt > 1 ? (int)(blockIdx.x % KA.nvirt) : 0;   // rank slot this CTA works for
+    const int bid = KA.nvirt > 1 ? (int)(blockIdx.x / KA.nvirt) : (int)blockIdx.x;
+    const Params &P = KA.rc[vr].P;
+    const CUtensorMap &mapA = KA.rc[vr].mapA;
+    const CUtensorMap *mapVs = KA.rc[vr].mapV;
     uint64_t *bars = reinterpret_cast<uint64_t *>(g_smem + C::OFF_BAR);
     uint64_t *full = bars, *computed = bars + C::NS, *empty = bars + 2 * C::NS, *pfull = bars + 3 * C::NS;
     int *s_task = reinterpret_cast<int *>(bars + 3 * C::NS + 2 * NPW);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const Watch wd{gtimer(), P.watchdog_ns};
     const bool split = P.npanel_ctas > 0;
-    const bool panel_cta = !split || (int)blockIdx.x < P.npanel_ctas;
-    const bool sweep_cta = !split || (int)blockIdx.x >= P.npanel_ctas;
+    const bool panel_cta = !split || bid < P.npanel_ctas;
+    const bool sweep_cta = !split || bid >= P.npanel_ctas;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::NS; ++s) {
@@ -401,7 +440,8 @@ tiledqr_persistent(const Params P, const __grid_constant__ CUtensorMap mapA, con
         }
         for (int i = 0; i < 2 * NPW; ++i) mbar_init(&pfull[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapV);
+        tma_prefetch_desc(&mapA);
+        for (int r = 0; r < P.world; ++r) tma_prefetch_desc(&mapVs[r]);
     }
     __syncthreads();
 
@@ -412,8 +452,8 @@ tiledqr_persistent(const Params P, const __grid_constant__ CUtensorMap mapA, con
             int t = 0;
             if (lane == 0) t = atomicAdd(&P.ctr[2], 1);
             t = __shfl_sync(FULL, t, 0);
-            if (t >= P.K) break;
-            run_panel<NC>(P, &mapA, t, warp - W_PANEL, phbits, wd);
+            if (t >= P.npanels) break;
+            run_panel<NC>(P, &mapA, P.panel_tab[t], warp - W_PANEL, phbits, wd);
         }
         return;
     }
@@ -431,7 +471,7 @@ tiledqr_persistent(const Params P, const __grid_constant__ CUtensorMap mapA, con
         named_bar_sync(1, SWEEP_THREADS);
         const int k = s_task[0], g = s_task[1];
         if (k < 0) break;
-        if (warp == W_LOADER) sweep_loader<NC>(P, &mapA, &mapV, k, g, cx, ring, wd);
+        if (warp == W_LOADER) sweep_loader<NC>(P, &mapA, mapVs, k, g, cx, ring, wd);
         else if (warp == W_STORER) sweep_storer<NC>(P, &mapA, k, g, cx, ring, wd);
         else sweep_consumer<NC>(P, k, g, cx, ring, wd);
     }
@@ -589,8 +629,14 @@ struct b200qr_plan_s {
     int m, n, p, q, K;
     int grid;
     int nc;                 // matrix columns per consumer thread (1 or 2): kernel variant
+    int G;                  // tile columns per sweep = distribution block
     int npanel_ctas;        // role split (0 = every CTA runs both roles)
-    int nsweeps;            // sweep tickets; panel tickets = K
+    int nsweeps, npanels;   // tickets of this rank
+    int rank = 0, world = 1;
+    float *peer_A[MAXW];
+    int *peer_prog[MAXW];
+    float *peer_tauc[MAXW];
+    int *d_panel_tab = nullptr;
     long tile_tasks;
     int trace;
     int *d_prog = nullptr, *d_ctr = nullptr, *d_trace = nullptr;
@@ -655,6 +701,13 @@ const char *b200qr_strerror(int code)
 
 int b200qr_last_cuda_error(void) { return g_last_cuda; }
 
+int b200qr_copy(void *dst, const void *src, size_t bytes)
+{
+    if (!dst || !src) return B200QR_EINVAL;
+    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
+    return B200QR_OK;
+}
+
 int b200qr_device_sm_count(void)
 {
     int dev = 0, sms = 0;
@@ -663,12 +716,12 @@ int b200qr_device_sm_count(void)
     return sms;
 }
 
-int b200qr_plan_create(b200qr_plan_t *out, int m, int n, const b200qr_opts *opts)
+// Builds the schedule + workspace of one rank (rank 0 of 1 = the plain single-GPU plan).
+static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int nvirt, const b200qr_opts *opts)
 {
-    if (!out || m <= 0 || n <= 0 || m % TB || n % TB) return B200QR_EINVAL;
-    b200qr_plan_s *pl = new b200qr_plan_s;
     pl->m = m; pl->n = n; pl->p = m / TB; pl->q = n / TB;
     pl->K = pl->p < pl->q ? pl->p : pl->q;
+    pl->rank = rank; pl->world = world;
     pl->trace = opts ? opts->trace : 0;
     const char *wd = getenv("QRB200_WATCHDOG_MS");
     pl->watchdog_ns = (unsigned long long)(wd ? atol(wd) : 60000) * 1000000ull;
@@ -686,55 +739,127 @@ int b200qr_plan_create(b200qr_plan_t *out, int m, int n, const b200qr_opts *opts
         CK(cudaFuncSetAttribute(kernel_of(nc), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(nc)));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel_of(2), NTHREADS, smem_of(2)));
-    if (occ < 1) { delete pl; return B200QR_EINVAL; }
-    int grid = occ * sms;                          // every CTA must be co-resident (cooperative launch)
+    if (occ < 1) return B200QR_EINVAL;
+    int grid = occ * sms / nvirt;                  // every CTA must be co-resident (cooperative launch)
     if (opts && opts->grid_ctas > 0 && opts->grid_ctas < grid) grid = opts->grid_ctas;
 
     // Kernel variant and roles.  Large grids split the roles: a few CTAs run only TSQRT chains
     // (two panel warps each, undisturbed by the FFMA-bound consumers), the rest only sweeps with
     // 2 matrix columns per consumer thread (16 tile columns per sweep).  The number of panel
     // warps sets how many panel chains advance at once: about (chain work) / (sweep work per
-    // warp-time), which is ~2800 / q panel chains on a B200.  Small grids (tests, tiny
-    // matrices) run both roles in every CTA with the 1-column variant.
+    // warp-time); measured on a B200 (13.7 us per TSQRT, 8.6 us per 16-tile sweep row) plus slack
+    // for the lock-step diagonal sweeps that is ~8000 / q panel chains.  Small grids (tests, tiny
+    // matrices) run both roles in every CTA with the 1-column variant.  With several ranks the
+    // variant must be the same everywhere (it fixes the distribution block), so it is derived
+    // from the shape and the world size only.
     pl->nc = 1; pl->npanel_ctas = 0;
-    if (grid >= 16 && q >= 32) {
+    const bool big = world > 1 ? q >= 32 * world : (grid >= 16 && q >= 32);
+    if (big && grid >= 16) {
         pl->nc = 2;
-        int want = (2800 / q + 2 + NPW - 1) / NPW;
+        int want = (8000 / q + 2 + NPW - 1) / NPW;
         if (want < 2) want = 2;
-        if (want > grid / 4) want = grid / 4;
+        if (want > grid / 5) want = grid / 5;
         pl->npanel_ctas = want;
     }
-    if (const char *e = getenv("QRB200_NP")) {
-        int v = atoi(e);
-        if (v > 0 && v < grid && grid >= 2) { pl->npanel_ctas = v; } else if (v == 0) { pl->npanel_ctas = 0; pl->nc = 1; }
+    if (world == 1) {
+        if (const char *e = getenv("QRB200_NP")) {
+            int v = atoi(e);
+            if (v > 0 && v < grid && grid >= 2) { pl->npanel_ctas = v; } else if (v == 0) { pl->npanel_ctas = 0; pl->nc = 1; }
+        }
+        if (const char *e = getenv("QRB200_NC")) { int v = atoi(e); if (v == 1 || (v == 2 && pl->npanel_ctas > 0)) pl->nc = v; }
+    } else if (pl->nc == 2 && grid < 16) {
+        return B200QR_EINVAL;                      // cannot honour the world-wide variant on this grid
     }
-    if (const char *e = getenv("QRB200_NC")) { int v = atoi(e); if (v == 1 || (v == 2 && pl->npanel_ctas > 0)) pl->nc = v; }
     const int G = CW * pl->nc;
+    pl->G = G;
 
-    // sweep tickets in skewed order (sched_host.cpp)
-    long cap = 0;
-    for (int k = 0; k < K; ++k) if (k + 1 < q) cap += (q + G - 1) / G - (k + 1) / G;
-    std::vector<int> tab(2 * (size_t)(cap > 0 ? cap : 1));
-    long ns = b200qr_sched_sweep_order(p, q, G, tab.data(), cap);
-    if (ns != cap) { delete pl; return B200QR_EINVAL; }
+    // this rank's tickets: sweeps of its blocks in the global skewed order, panels of its tile columns
+    long npan = 0;
+    const long ns = b200qr_sched_rank_tickets(p, q, G, rank, world, nullptr, 0, nullptr, 0, &npan);
+    if (ns < 0) return B200QR_EINVAL;
+    std::vector<int> tab(2 * (size_t)(ns > 0 ? ns : 1)), ptab((size_t)(npan > 0 ? npan : 1));
+    b200qr_sched_rank_tickets(p, q, G, rank, world, tab.data(), ns, ptab.data(), npan, &npan);
+    ptab.resize((size_t)npan);
     pl->nsweeps = (int)ns;
-    const int useful = (pl->nsweeps > K ? pl->nsweeps : K) + pl->npanel_ctas;
-    if (grid > useful) grid = useful;
+    pl->npanels = (int)npan;
+    const int useful = (pl->nsweeps > pl->npanels ? pl->nsweeps : pl->npanels) + pl->npanel_ctas;
+    if (grid > useful) grid = useful > 0 ? useful : 1;
     if (pl->npanel_ctas >= grid) pl->npanel_ctas = grid > 1 ? grid / 2 : 0;
-    if (pl->npanel_ctas == 0) pl->nc = 1;
+    if (pl->npanel_ctas == 0) {
+        if (pl->nc == 2 && world > 1) return B200QR_EINVAL;
+        pl->nc = 1;
+    }
     pl->grid = grid;
 
     CK(cudaMalloc(&pl->d_prog, sizeof(int) * (size_t)p * q));
     CK(cudaMalloc(&pl->d_ctr, sizeof(int) * 64));
     CK(cudaMalloc(&pl->d_sweep_tab, sizeof(int2) * (size_t)(ns > 0 ? ns : 1)));
     if (ns > 0) CK(cudaMemcpy(pl->d_sweep_tab, tab.data(), sizeof(int2) * (size_t)ns, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&pl->d_panel_tab, sizeof(int) * (ptab.size() ? ptab.size() : 1)));
+    if (!ptab.empty()) CK(cudaMemcpy(pl->d_panel_tab, ptab.data(), sizeof(int) * ptab.size(), cudaMemcpyHostToDevice));
     CK(cudaMalloc(&pl->d_tauc, sizeof(float) * (size_t)K * p * TB));
     CK(cudaMemset(pl->d_tauc, 0, sizeof(float) * (size_t)K * p * TB));
+    CK(cudaMemset(pl->d_prog, 0, sizeof(int) * (size_t)p * q));
     if (pl->trace) {
         CK(cudaMalloc(&pl->d_trace, sizeof(int) * 2 * (size_t)tiles));
         CK(cudaMalloc(&pl->d_trace_off, sizeof(long long) * K));
         CK(cudaMemcpy(pl->d_trace_off, pl->trace_off.data(), sizeof(long long) * K, cudaMemcpyHostToDevice));
     }
+    for (int r = 0; r < MAXW; ++r) { pl->peer_A[r] = nullptr; pl->peer_prog[r] = nullptr; pl->peer_tauc[r] = nullptr; }
+    pl->peer_prog[rank] = pl->d_prog; pl->peer_tauc[rank] = pl->d_tauc;
+    return B200QR_OK;
+}
+
+static void plan_free(b200qr_plan_s *pl)
+{
+    cudaFree(pl->d_prog); cudaFree(pl->d_ctr); cudaFree(pl->d_sweep_tab); cudaFree(pl->d_panel_tab); cudaFree(pl->d_tauc);
+    cudaFree(pl->d_trace); cudaFree(pl->d_trace_off);
+}
+
+// Fills one rank slot of the kernel arguments (dA/ldm = this rank's matrix).
+static int fill_rank_ctx(RankCtx *rc, b200qr_plan_s *pl, float *dA, int ldm)
+{
+    Params &P = rc->P;
+    memset(&P, 0, sizeof P);
+    P.A = dA; P.ldm = ldm; P.p = pl->p; P.q = pl->q; P.K = pl->K;
+    P.tauc = pl->d_tauc; P.prog = pl->d_prog; P.ctr = pl->d_ctr;
+    P.sweep_tab = pl->d_sweep_tab; P.nsweeps = pl->nsweeps; P.npanel_ctas = pl->npanel_ctas;
+    P.panel_tab = pl->d_panel_tab; P.npanels = pl->npanels;
+    P.rank = pl->rank; P.world = pl->world;
+    P.trace = pl->trace ? pl->d_trace : nullptr; P.trace_off = pl->d_trace_off; P.trace_mode = pl->trace;
+    P.watchdog_ns = pl->watchdog_ns;
+    for (int r = 0; r < pl->world; ++r) { P.peer_prog[r] = pl->peer_prog[r]; P.peer_tauc[r] = pl->peer_tauc[r]; }
+    int rc_ = make_tile_map(&rc->mapA, dA, pl->m, pl->n, ldm, true);
+    for (int r = 0; r < pl->world && rc_ == B200QR_OK; ++r) {
+        float *src = r == pl->rank ? dA : pl->peer_A[r];
+        int ld = r == pl->rank ? ldm : pl->m;
+        if (!src) return B200QR_EINVAL;            // peers not connected
+        rc_ = make_tile_map(&rc->mapV[r], src, pl->m, pl->n, ld, false);
+    }
+    return rc_;
+}
+
+static int reset_progress(b200qr_plan_s *pl, cudaStream_t stream)
+{
+    CK(cudaMemsetAsync(pl->d_prog, 0, sizeof(int) * (size_t)pl->p * pl->q, stream));
+    CK(cudaMemsetAsync(pl->d_ctr, 0, sizeof(int) * 64, stream));
+    if (pl->trace) CK(cudaMemsetAsync(pl->d_trace, 0xff, sizeof(int) * 2 * (size_t)pl->tile_tasks, stream));
+    return B200QR_OK;
+}
+
+static int launch(KernelArgs *ka, int nc, int grid, cudaStream_t stream)
+{
+    void *args[] = {ka};
+    CK(cudaLaunchCooperativeKernel(kernel_of(nc), dim3(grid), dim3(NTHREADS), args, smem_of(nc), stream));
+    return B200QR_OK;
+}
+
+int b200qr_plan_create(b200qr_plan_t *out, int m, int n, const b200qr_opts *opts)
+{
+    if (!out || m <= 0 || n <= 0 || m % TB || n % TB) return B200QR_EINVAL;
+    b200qr_plan_s *pl = new b200qr_plan_s;
+    int rc = plan_build(pl, m, n, 0, 1, 1, opts);
+    if (rc != B200QR_OK) { plan_free(pl); delete pl; return rc; }
     *out = pl;
     return B200QR_OK;
 }
@@ -742,37 +867,158 @@ int b200qr_plan_create(b200qr_plan_t *out, int m, int n, const b200qr_opts *opts
 int b200qr_plan_destroy(b200qr_plan_t pl)
 {
     if (!pl) return B200QR_EINVAL;
-    cudaFree(pl->d_prog); cudaFree(pl->d_ctr); cudaFree(pl->d_sweep_tab); cudaFree(pl->d_tauc);
-    cudaFree(pl->d_trace); cudaFree(pl->d_trace_off);
+    plan_free(pl);
     delete pl;
     return B200QR_OK;
 }
 
 int b200qr_plan_grid(b200qr_plan_t pl) { return pl ? pl->grid : B200QR_EINVAL; }
 long b200qr_plan_tile_tasks(b200qr_plan_t pl) { return pl ? pl->tile_tasks : B200QR_EINVAL; }
-long b200qr_plan_macro_tasks(b200qr_plan_t pl) { return pl ? (long)pl->nsweeps + pl->K : B200QR_EINVAL; }
+long b200qr_plan_macro_tasks(b200qr_plan_t pl) { return pl ? (long)pl->nsweeps + pl->npanels : B200QR_EINVAL; }
 const float *b200qr_plan_tau_device(b200qr_plan_t pl) { return pl ? pl->d_tauc : nullptr; }
 
 int b200qr_factor_device(b200qr_plan_t pl, float *dA, int ldm, void *stream_)
 {
-    if (!pl || !dA || ldm < pl->m || (ldm & 3) || ((uintptr_t)dA & 15)) return B200QR_EINVAL;
+    if (!pl || pl->world != 1 || !dA || ldm < pl->m || (ldm & 3) || ((uintptr_t)dA & 15)) return B200QR_EINVAL;
     cudaStream_t stream = (cudaStream_t)stream_;
-    CK(cudaMemsetAsync(pl->d_prog, 0, sizeof(int) * (size_t)pl->p * pl->q, stream));
-    CK(cudaMemsetAsync(pl->d_ctr, 0, sizeof(int) * 64, stream));
-    if (pl->trace) CK(cudaMemsetAsync(pl->d_trace, 0xff, sizeof(int) * 2 * (size_t)pl->tile_tasks, stream));
-    Params P;
-    P.A = dA; P.ldm = ldm; P.p = pl->p; P.q = pl->q; P.K = pl->K;
-    P.tauc = pl->d_tauc; P.prog = pl->d_prog; P.ctr = pl->d_ctr;
-    P.sweep_tab = pl->d_sweep_tab; P.nsweeps = pl->nsweeps; P.npanel_ctas = pl->npanel_ctas;
-    P.trace = pl->trace ? pl->d_trace : nullptr; P.trace_off = pl->d_trace_off; P.trace_mode = pl->trace;
-    P.watchdog_ns = pl->watchdog_ns;
-    CUtensorMap mapA, mapV;                        // swizzled (thread-per-column tiles) / dense (reflector tiles)
-    int rc = make_tile_map(&mapA, dA, pl->m, pl->n, ldm, true);
-    if (rc == B200QR_OK) rc = make_tile_map(&mapV, dA, pl->m, pl->n, ldm, false);
+    int rc = reset_progress(pl, stream);
     if (rc != B200QR_OK) return rc;
-    void *args[] = {&P, &mapA, &mapV};
-    CK(cudaLaunchCooperativeKernel(kernel_of(pl->nc), dim3(pl->grid), dim3(NTHREADS), args, smem_of(pl->nc), stream));
+    KernelArgs ka;
+    ka.nvirt = 1;
+    rc = fill_rank_ctx(&ka.rc[0], pl, dA, ldm);
+    if (rc != B200QR_OK) return rc;
+    return launch(&ka, pl->nc, pl->grid, stream);
+}
+
+// ---------------------------------------------------------------- multi-GPU (one rank per process)
+struct b200qr_dist_s {
+    b200qr_plan_s plan;
+    float *dA = nullptr;            // this rank's m x n matrix (ld = m); only the owned tile columns are used
+    void *opened[3 * MAXW] = {};    // IPC mappings to close
+    int connected = 0;
+};
+
+struct ipc_blob { cudaIpcMemHandle_t a, prog, tauc; };
+
+int b200qr_dist_handle_bytes(void) { return (int)sizeof(ipc_blob); }
+
+int b200qr_dist_create(b200qr_dist_t *out, int m, int n, int rank, int world, const b200qr_opts *opts)
+{
+    if (!out || m <= 0 || n <= 0 || m % TB || n % TB || world < 1 || world > MAXW || rank < 0 || rank >= world)
+        return B200QR_EINVAL;
+    b200qr_dist_s *d = new b200qr_dist_s;
+    int nvirt = opts && opts->share_device > 1 ? opts->share_device : 1;    // ranks sharing this device (emulation)
+    int rc = plan_build(&d->plan, m, n, rank, world, nvirt, opts);
+    if (rc == B200QR_OK && cudaMalloc(&d->dA, sizeof(float) * (size_t)m * n) != cudaSuccess) rc = B200QR_ENOMEM;
+    if (rc != B200QR_OK) { plan_free(&d->plan); cudaFree(d->dA); delete d; return rc; }
+    d->plan.peer_A[rank] = d->dA;
+    if (world == 1) d->connected = 1;
+    *out = d;
     return B200QR_OK;
+}
+
+int b200qr_dist_destroy(b200qr_dist_t d)
+{
+    if (!d) return B200QR_EINVAL;
+    for (void *ptr : d->opened) if (ptr) cudaIpcCloseMemHandle(ptr);
+    plan_free(&d->plan);
+    cudaFree(d->dA);
+    delete d;
+    return B200QR_OK;
+}
+
+float *b200qr_dist_matrix(b200qr_dist_t d) { return d ? d->dA : nullptr; }
+int b200qr_dist_block(b200qr_dist_t d) { return d ? d->plan.G : B200QR_EINVAL; }
+int b200qr_dist_owner(b200qr_dist_t d, int tile_col) { return d ? (tile_col / d->plan.G) % d->plan.world : B200QR_EINVAL; }
+int b200qr_dist_grid(b200qr_dist_t d) { return d ? d->plan.grid : B200QR_EINVAL; }
+const float *b200qr_dist_tau_device(b200qr_dist_t d) { return d ? d->plan.d_tauc : nullptr; }
+
+int b200qr_dist_export(b200qr_dist_t d, void *out_bytes)
+{
+    if (!d || !out_bytes) return B200QR_EINVAL;
+    ipc_blob b;
+    CK(cudaIpcGetMemHandle(&b.a, d->dA));
+    CK(cudaIpcGetMemHandle(&b.prog, d->plan.d_prog));
+    CK(cudaIpcGetMemHandle(&b.tauc, d->plan.d_tauc));
+    memcpy(out_bytes, &b, sizeof b);
+    return B200QR_OK;
+}
+
+int b200qr_dist_connect(b200qr_dist_t d, const void *all_bytes)
+{
+    if (!d || !all_bytes) return B200QR_EINVAL;
+    const ipc_blob *blobs = (const ipc_blob *)all_bytes;
+    b200qr_plan_s &pl = d->plan;
+    for (int r = 0; r < pl.world; ++r) {
+        if (r == pl.rank) continue;
+        void *a = nullptr, *pr = nullptr, *tc = nullptr;
+        CK(cudaIpcOpenMemHandle(&a, blobs[r].a, cudaIpcMemLazyEnablePeerAccess));
+        CK(cudaIpcOpenMemHandle(&pr, blobs[r].prog, cudaIpcMemLazyEnablePeerAccess));
+        CK(cudaIpcOpenMemHandle(&tc, blobs[r].tauc, cudaIpcMemLazyEnablePeerAccess));
+        d->opened[3 * r] = a; d->opened[3 * r + 1] = pr; d->opened[3 * r + 2] = tc;
+        pl.peer_A[r] = (float *)a; pl.peer_prog[r] = (int *)pr; pl.peer_tauc[r] = (float *)tc;
+    }
+    d->connected = 1;
+    return B200QR_OK;
+}
+
+// Same-process wiring of `world` rank objects that live on ONE device (tests, and the emulation
+// the profiling guide asks for when there are fewer GPUs than ranks).
+int b200qr_dist_connect_local(b200qr_dist_t *all, int world)
+{
+    if (!all || world < 1 || world > MAXW) return B200QR_EINVAL;
+    for (int r = 0; r < world; ++r) {
+        if (!all[r] || all[r]->plan.world != world || all[r]->plan.rank != r) return B200QR_EINVAL;
+        for (int o = 0; o < world; ++o) {
+            all[r]->plan.peer_A[o] = all[o]->dA;
+            all[r]->plan.peer_prog[o] = all[o]->plan.d_prog;
+            all[r]->plan.peer_tauc[o] = all[o]->plan.d_tauc;
+        }
+        all[r]->connected = 1;
+    }
+    return B200QR_OK;
+}
+
+// Zero this rank's progress words / ticket counters.  Every rank must have done this (and the
+// ranks must have synchronised, e.g. a torch.distributed barrier) before any rank launches.
+int b200qr_dist_reset(b200qr_dist_t d, void *stream)
+{
+    if (!d) return B200QR_EINVAL;
+    return reset_progress(&d->plan, (cudaStream_t)stream);
+}
+
+// Launch this rank's persistent kernel (asynchronous).  The kernels of all ranks run at the same
+// time, one per GPU, and read each other's reflector tiles over NVLink.
+int b200qr_dist_factor(b200qr_dist_t d, void *stream)
+{
+    if (!d || !d->connected) return B200QR_EINVAL;
+    KernelArgs ka;
+    ka.nvirt = 1;
+    int rc = fill_rank_ctx(&ka.rc[0], &d->plan, d->dA, d->plan.m);
+    if (rc != B200QR_OK) return rc;
+    return launch(&ka, d->plan.nc, d->plan.grid, (cudaStream_t)stream);
+}
+
+// All ranks of a locally wired group in ONE cooperative launch on the current device: CTA b works
+// for rank b % world.  (Separate launches that wait on each other must not share a GPU.)
+int b200qr_dist_factor_group(b200qr_dist_t *all, int world, void *stream_)
+{
+    if (!all || world < 1 || world > MAXV) return B200QR_EINVAL;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    KernelArgs ka;
+    ka.nvirt = world;
+    int grid = 1 << 30;
+    for (int r = 0; r < world; ++r) {
+        if (!all[r] || !all[r]->connected || all[r]->plan.nc != all[0]->plan.nc) return B200QR_EINVAL;
+        int rc = reset_progress(&all[r]->plan, stream);
+        if (rc == B200QR_OK) rc = fill_rank_ctx(&ka.rc[r], &all[r]->plan, all[r]->dA, all[r]->plan.m);
+        if (rc != B200QR_OK) return rc;
+        if (all[r]->plan.grid < grid) grid = all[r]->plan.grid;
+    }
+    // one common per-rank grid: the role split must fit it
+    for (int r = 0; r < world; ++r)
+        if (ka.rc[r].P.npanel_ctas >= grid) return B200QR_EINVAL;
+    return launch(&ka, all[0]->plan.nc, grid * world, stream);
 }
 
 int b200qr_tau_to_reference(b200qr_plan_t pl, float *dTauMat, int ldtau, void *stream_)

@@ -156,6 +156,36 @@ long b200qr_sched_sweep_order(int M, int N, int G, int *out2, long cap)
     return n;
 }
 
+// Tickets of one rank of the 1-D block-cyclic distribution (block = G tile columns, block g on
+// rank g % world): the sweeps of its blocks, in the global skewed order, and the panels of its
+// tile columns, ascending.  Every rank's streams are subsequences of the global streams, so the
+// deadlock-freedom argument carries over unchanged.  Returns the sweep count; *npanels gets the
+// panel count (either output array may be NULL to just count).
+long b200qr_sched_rank_tickets(int M, int N, int G, int rank, int world, int *sweeps2, long cap, int *panels, long capp,
+                               long *npanels)
+{
+    if (world < 1 || rank < 0 || rank >= world) return -1;
+    long total = b200qr_sched_sweep_order(M, N, G, nullptr, 0);
+    if (total < 0) return -1;
+    std::vector<int> all(2 * (size_t)(total > 0 ? total : 1));
+    b200qr_sched_sweep_order(M, N, G, all.data(), total);
+    long n = 0;
+    for (long t = 0; t < total; ++t)
+        if (all[2 * t + 1] % world == rank) {
+            if (sweeps2 && n < cap) { sweeps2[2 * n] = all[2 * t]; sweeps2[2 * n + 1] = all[2 * t + 1]; }
+            ++n;
+        }
+    const int K = M < N ? M : N;
+    long np = 0;
+    for (int k = 0; k < K; ++k)
+        if ((k / G) % world == rank) {
+            if (panels && np < capp) panels[np] = k;
+            ++np;
+        }
+    if (npanels) *npanels = np;
+    return n;
+}
+
 // One serial order that is consistent with both ticket streams of the persistent kernel (panel
 // tickets P(0), P(1), ...; sweep tickets as above), expanded to tile tasks (n x 4 ints: type,l,m,k):
 // each panel is emitted just before the first sweep that needs it.  Tests check that this is a

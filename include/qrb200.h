@@ -55,7 +55,9 @@ typedef struct {
     int grid_ctas;      /* persistent grid size; 0 = all co-resident CTAs of the device     */
     int trace;          /* 1 = record a per-tile-task start/finish sequence (DAG tests);
                            2 = record %globaltimer nanoseconds (low 32 bits) instead            */
-    int reserved[6];
+    int share_device;   /* b200qr_dist_create only: number of rank objects that will share this device
+                           and be launched together with b200qr_dist_factor_group (0/1 = none)    */
+    int reserved[5];
 } b200qr_opts;
 
 typedef struct b200qr_plan_s *b200qr_plan_t;
@@ -65,6 +67,9 @@ int         b200qr_version(void);
 const char *b200qr_strerror(int code);
 int         b200qr_last_cuda_error(void);        /* cudaError_t of the last B200QR_ECUDA */
 int         b200qr_device_sm_count(void);
+/* Synchronous copy between any two host/device buffers (cudaMemcpyDefault): lets a caller fill and
+ * read the library-owned matrices of the multi-GPU API without linking the CUDA runtime itself. */
+int         b200qr_copy(void *dst, const void *src, size_t bytes);
 /* Measured FP32 FFMA throughput of the current device in GFLOP/s (register-resident FMA loop
  * on every SM, best of 3 after a warm-up): the roofline denominator of the SIMT kernels.   */
 int         b200qr_measure_fp32_peak(double *gflops, int iters);
@@ -101,6 +106,36 @@ int b200qr_tau_to_reference(b200qr_plan_t plan, float *dTauMat, int ldtau, void 
  * kernel_ms (optional) receives the device time of the factorisation only.         */
 int b200qr_factor_host(float *hA, int m, int n, int ldm, float *hTauMat, float *kernel_ms);
 
+/* ---- multi-GPU: 1-D block-cyclic tile columns, one rank (process) per GPU -----------------------
+ * The reference is single-GPU; this is the north-star extension.  Tile columns are dealt to the
+ * ranks in blocks of b200qr_dist_block() tile columns (block g to rank g % world).  Every rank
+ * runs the same persistent kernel on its own GPU: the panels of its tile columns and the sweeps
+ * of its blocks.  The reflector tiles, tau and panel progress words of a step whose panel lives
+ * on another rank are read directly from that rank's memory over NVLink inside the kernel (peer
+ * mappings obtained with CUDA IPC), so there is no host-side broadcast step.
+ *
+ * Protocol (all ranks):  create -> export -> [exchange the handle bytes, e.g. all_gather] ->
+ * connect -> fill the owned columns of b200qr_dist_matrix() -> reset -> [barrier] -> factor ->
+ * [stream sync].  Results (R and V of the owned tile columns, tau of the owned panels) stay in
+ * the rank's matrix / tau buffer.                                                                */
+typedef struct b200qr_dist_s *b200qr_dist_t;
+int    b200qr_dist_create(b200qr_dist_t *d, int m, int n, int rank, int world, const b200qr_opts *opts);
+int    b200qr_dist_destroy(b200qr_dist_t d);
+int    b200qr_dist_handle_bytes(void);                       /* size of one rank's exported handle blob */
+int    b200qr_dist_export(b200qr_dist_t d, void *out_bytes);
+int    b200qr_dist_connect(b200qr_dist_t d, const void *all_bytes);   /* world blobs, rank order */
+float *b200qr_dist_matrix(b200qr_dist_t d);                  /* device pointer, m x n, leading dimension m */
+const float *b200qr_dist_tau_device(b200qr_dist_t d);        /* compact tau [(k*p + i)*32 + r], owned panels */
+int    b200qr_dist_block(b200qr_dist_t d);                   /* tile columns per distribution block */
+int    b200qr_dist_owner(b200qr_dist_t d, int tile_col);     /* rank that owns a tile column */
+int    b200qr_dist_grid(b200qr_dist_t d);
+int    b200qr_dist_reset(b200qr_dist_t d, void *stream);
+int    b200qr_dist_factor(b200qr_dist_t d, void *stream);
+/* Same-process variants for rank objects that share ONE device (tests / fewer GPUs than ranks):
+ * wire them with plain pointers and run all of them in a single cooperative launch (world <= 2). */
+int    b200qr_dist_connect_local(b200qr_dist_t *all, int world);
+int    b200qr_dist_factor_group(b200qr_dist_t *all, int world, void *stream);
+
 /* ---- trace of the device scheduler (opts.trace = 1) -------------------------------
  * For every tile task (k, i, j) the kernel records a global sequence number when the
  * task starts reading its inputs and when its outputs are published.  Records come
@@ -131,6 +166,10 @@ int  b200qr_sched_predecessors(const b200qr_task *t, b200qr_task pred[3]);
 /* Sweep ticket order of the persistent kernel for an M x N tile grid and G tile columns per
  * sweep: (k, g) pairs sorted by k + G*g.  Returns the number of sweeps (out2 may be NULL).    */
 long b200qr_sched_sweep_order(int M, int N, int G, int *out2, long cap);
+/* Tickets of one rank of the block-cyclic distribution (block g of G tile columns on rank g % world):
+ * its sweeps (k, g) in the global order and its panels k, ascending.  Returns the sweep count.  */
+long b200qr_sched_rank_tickets(int M, int N, int G, int rank, int world, int *sweeps2, long cap, int *panels,
+                               long capp, long *npanels);
 /* One serial order consistent with both ticket streams of the device scheduler, expanded to
  * tile tasks (n x 4 ints: type,l,m,k).                                               */
 long b200qr_sched_device_order(int M, int N, int *out4, long cap);
