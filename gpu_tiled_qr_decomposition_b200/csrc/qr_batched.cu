@@ -1,0 +1,279 @@
+// qr_batched.cu -- many small tiled QR factorisations at once, and the TSQR tree built on them.
+//
+// BASELINE.json configs[2] (10 000 independent 256x256 matrices) and configs[3] (tall-skinny
+// 4 194 304 x 256, TSQR/CAQR reduction tree).  Each problem is the reference's tile algorithm
+// unchanged (same four tile kernels, same flat tree inside a problem, same output layout: R above,
+// GEQRT / TSQRT reflectors below, tau per reflector), so a 256x256 problem of the batch equals
+// cudaQRTask on that matrix.  What changes is the schedule: a problem has at most 8 tile columns,
+// so ONE CTA factors it with a static assignment -- warp w owns tile column w: it applies the
+// panels of the steps k < w to its column (UNMQR + TSMQR chain, the step's tile row k resident
+// in shared memory), then factors its own column (GEQRT + TSQRT chain) and retires.  Warps follow
+// each other through per-step progress counters in shared memory (the tile-DAG dependencies of
+// gridscheduler.c:112-174 collapse to "panel k has finished tile row i").  CTAs pull problems from
+// an atomic counter; three CTAs share an SM, so one problem's idle warps are another's busy ones.
+//
+// TSQR: the rows are cut into leaves (leaf_rows x n, a batch), every leaf is factored as above, the
+// leaves' R factors are stacked and factored again, `fanin` at a time, until one R is left.  The
+// implicit Q is the tree of reflector sets (leaves in place in A, inner nodes in the plan's
+// workspace) -- a different Householder layout from the reference's flat chain, as SURVEY 8e
+// notes; parity for this path is on R (up to row signs) and on R^T R = A^T A.
+#include "qr_device.cuh"
+#include "../../include/qrb200.h"
+
+#include <cstdlib>
+#include <vector>
+
+namespace qrb200 {
+
+constexpr int BQ = 8;                       // max tile columns per problem = warps per CTA
+constexpr int WARP_FLOATS = 1088 + 1024 + 32 + 64;   // V/Rs, top row, tau, broadcast slots
+
+struct BatchArgs {
+    float *A;
+    long long strideA;      // elements between consecutive problems
+    int ldm, p, q, nprob;
+    float *tauc;            // nprob x K*p*32, compact per problem: [(k*p + i)*32 + r]
+    int *counter;
+};
+
+__device__ __forceinline__ void spin_ge(volatile int *flag, int target)
+{
+    while (*flag < target) __nanosleep(20);
+}
+
+__global__ void __launch_bounds__(BQ * 32, 2) batched_tiledqr_kernel(const BatchArgs a)
+{
+    extern __shared__ __align__(16) float bsm[];
+    __shared__ int s_prob;
+    __shared__ volatile int panel_prog[BQ];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *Vs = bsm + w * WARP_FLOATS;      // reflector tile of the current row; Rs while this warp is the panel
+    float *top = Vs + 1088;                 // tile row k of my column: top[c*32 + lane]
+    float *ts = top + 1024;
+    float *xs = ts + 32;
+    const int p = a.p, q = a.q, K = p < q ? p : q, ldm = a.ldm;
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_prob = atomicAdd(a.counter, 1);
+        if (threadIdx.x < BQ) panel_prog[threadIdx.x] = 0;
+        __syncthreads();
+        const int b = s_prob;
+        if (b >= a.nprob) break;
+        if (w >= q) continue;
+        float *M = a.A + (size_t)b * a.strideA;
+        float *tb = a.tauc + (size_t)b * K * p * TB;
+        auto tile = [&](int I, int J) { return M + (size_t)(J * TB + lane) * ldm + I * TB; };
+
+        for (int k = 0; k < K; ++k) {
+            float x[TB];
+            if (k == w) {
+                // ---- my panel: GEQRT + TSQRT chain (qrdecomp.c:532-557, 689-721)
+                load_col_gmem(x, tile(k, k));
+                float t = geqrt_warp(x, xs, lane);
+                store_col_gmem(tile(k, k), x);
+                tb[((size_t)k * p + k) * TB + lane] = t;
+#pragma unroll
+                for (int r = 0; r < TB; ++r) Vs[r * 33 + lane] = x[r];
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) panel_prog[k] = 1;
+                for (int i = k + 1; i < p; ++i) {
+                    load_col_gmem(x, tile(i, k));
+                    float ti = tsqrt_warp(x, Vs, xs, lane);
+                    store_col_gmem(tile(i, k), x);
+                    tb[((size_t)k * p + i) * TB + lane] = ti;
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) panel_prog[k] = i - k + 1;
+                }
+                float *rcol = tile(k, k);
+#pragma unroll
+                for (int r = 0; r < TB; ++r)
+                    if (r <= lane) rcol[r] = Vs[r * 33 + lane];
+                break;                                   // columns <= k have no work after step k
+            }
+            // ---- step k applied to my column: UNMQR + TSMQR chain (qrdecomp.c:620-644, 736-762)
+            for (int i = k; i < p; ++i) {
+                spin_ge(&panel_prog[k], i - k + 1);
+                load_col_gmem(x, tile(i, k));            // reflector tile (L2; written by warp k)
+                store_col_smem(Vs + lane * TB, x);
+                ts[lane] = __ldcg(tb + ((size_t)k * p + i) * TB + lane);
+                __syncwarp();
+                load_col_gmem(x, tile(i, w));
+                if (i == k) {
+                    apply_reflectors_nc<1, false>(x, x, nullptr, nullptr, 0, Vs, ts);
+#pragma unroll
+                    for (int r = 0; r < TB; ++r) top[r * TB + lane] = x[r];
+                } else {
+                    apply_reflectors_nc<1, true>(x, x, top + lane, top + lane, TB, Vs, ts);
+                    store_col_gmem(tile(i, w), x);
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int r = 0; r < TB; ++r) x[r] = top[r * TB + lane];
+            store_col_gmem(tile(k, w), x);
+        }
+    }
+}
+
+// stack the R factors (upper triangle of the top n x n of each problem) of a level into the next
+// level's input: dst is (nprob*n) x n, column-major, leading dimension nprob*n
+__global__ void gather_r_kernel(const float *src, long long strideA, int ldm, int n, int nprob, float *dst)
+{
+    const long long total = (long long)nprob * n * n;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        int r = (int)(e % n);
+        long long t = e / n;
+        int b = (int)(t % nprob), c = (int)(t / nprob);
+        float v = r <= c ? src[(size_t)b * strideA + (size_t)c * ldm + r] : 0.f;
+        dst[(size_t)c * ((size_t)nprob * n) + (size_t)b * n + r] = v;
+    }
+}
+
+}  // namespace qrb200
+
+using namespace qrb200;
+
+static thread_local int g_batched_cuda = 0;
+#define CKB(call)                                                           \
+    do {                                                                    \
+        cudaError_t e_ = (call);                                            \
+        if (e_ != cudaSuccess) { g_batched_cuda = (int)e_; return B200QR_ECUDA; } \
+    } while (0)
+
+static int batched_launch(float *dA, int m, int n, int ldm, long long strideA, int nprob, float *dTau, int *dCounter,
+                          cudaStream_t stream)
+{
+    static int grid_cap = 0;
+    const int smem = BQ * WARP_FLOATS * (int)sizeof(float);
+    if (!grid_cap) {
+        int dev = 0, sms = 0, occ = 0;
+        CKB(cudaGetDevice(&dev));
+        CKB(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        CKB(cudaFuncSetAttribute(batched_tiledqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, batched_tiledqr_kernel, BQ * 32, smem));
+        grid_cap = sms * (occ > 0 ? occ : 1);
+    }
+    BatchArgs a;
+    a.A = dA; a.strideA = strideA; a.ldm = ldm; a.p = m / TB; a.q = n / TB; a.nprob = nprob;
+    a.tauc = dTau; a.counter = dCounter;
+    CKB(cudaMemsetAsync(dCounter, 0, sizeof(int), stream));
+    const int grid = nprob < grid_cap ? nprob : grid_cap;
+    batched_tiledqr_kernel<<<grid, BQ * 32, smem, stream>>>(a);
+    CKB(cudaGetLastError());
+    return B200QR_OK;
+}
+
+struct b200qr_tsqr_s {
+    long long m;
+    int n, leaf_rows, fanin;
+    int *d_counter = nullptr;
+    float *d_leaf_tau = nullptr;
+    struct Level { long long count; int nfull, rest; float *stack = nullptr, *tau = nullptr; };
+    std::vector<Level> levels;          // reduction levels: `count` R factors in, nfull + (rest > 0) out
+};
+
+extern "C" {
+
+int b200qr_batched_workspace_floats(int m, int n, int nprob, long long *tau_floats)
+{
+    if (m <= 0 || n <= 0 || m % TB || n % TB || n > BQ * TB || nprob <= 0 || !tau_floats) return B200QR_EINVAL;
+    const int p = m / TB, q = n / TB, K = p < q ? p : q;
+    *tau_floats = (long long)nprob * K * p * TB;
+    return B200QR_OK;
+}
+
+// nprob independent m x n problems (n <= 256), problem b at dA + b*strideA, in place; dTau receives
+// nprob x K*p*32 floats (compact tau per problem); dCounter is one int of device scratch.
+int b200qr_batched_factor(float *dA, int m, int n, int ldm, long long strideA, int nprob, float *dTau, int *dCounter,
+                          void *stream)
+{
+    if (!dA || !dTau || !dCounter || m <= 0 || n <= 0 || m % TB || n % TB || n > BQ * TB || ldm < m || (ldm & 3) ||
+        ((uintptr_t)dA & 15) || (strideA & 3) || nprob <= 0)
+        return B200QR_EINVAL;
+    return batched_launch(dA, m, n, ldm, strideA, nprob, dTau, dCounter, (cudaStream_t)stream);
+}
+
+int b200qr_batched_last_cuda_error(void) { return g_batched_cuda; }
+
+// ---- TSQR ------------------------------------------------------------------------------------
+// Level structure: `count` R factors (n x n) are stacked into a (count*n) x n matrix and factored in
+// groups of `fanin` consecutive factors (one batched problem of fanin*n rows each; a shorter last
+// group of >= 2 factors is its own problem, a single left-over factor passes through).  The group
+// tops, all fanin*n rows apart, are the next level's R factors.
+int b200qr_tsqr_create(b200qr_tsqr_t *out, long long m, int n, int leaf_rows, int fanin)
+{
+    if (!out || n <= 0 || n % TB || n > BQ * TB || leaf_rows < n || leaf_rows % TB || m <= 0 || m % leaf_rows ||
+        fanin < 2 || fanin > 64)
+        return B200QR_EINVAL;
+    b200qr_tsqr_s *t = new b200qr_tsqr_s;
+    t->m = m; t->n = n; t->leaf_rows = leaf_rows; t->fanin = fanin;
+    const int q = n / TB;
+    const long long nleaf = m / leaf_rows;
+    auto fail = [&]() { b200qr_tsqr_destroy(t); return B200QR_ENOMEM; };
+    if (cudaMalloc(&t->d_counter, sizeof(int)) != cudaSuccess) return fail();
+    if (cudaMalloc(&t->d_leaf_tau, sizeof(float) * (size_t)nleaf * q * (leaf_rows / TB) * TB) != cudaSuccess) return fail();
+    long long count = nleaf;
+    while (count > 1) {
+        b200qr_tsqr_s::Level L;
+        L.count = count;
+        L.nfull = (int)(count / fanin);
+        L.rest = (int)(count % fanin);
+        if (cudaMalloc(&L.stack, sizeof(float) * (size_t)count * n * n) != cudaSuccess) return fail();
+        // tau: q * (rows/32) * 32 floats per problem = q * rows floats
+        size_t taufl = (size_t)L.nfull * q * fanin * n + (size_t)q * (L.rest > 0 ? L.rest : 1) * n;
+        if (cudaMalloc(&L.tau, sizeof(float) * taufl) != cudaSuccess) { cudaFree(L.stack); return fail(); }
+        t->levels.push_back(L);
+        count = L.nfull + (L.rest > 0 ? 1 : 0);
+    }
+    *out = t;
+    return B200QR_OK;
+}
+
+int b200qr_tsqr_destroy(b200qr_tsqr_t t)
+{
+    if (!t) return B200QR_EINVAL;
+    cudaFree(t->d_counter); cudaFree(t->d_leaf_tau);
+    for (auto &L : t->levels) { cudaFree(L.stack); cudaFree(L.tau); }
+    delete t;
+    return B200QR_OK;
+}
+
+int b200qr_tsqr_levels(b200qr_tsqr_t t) { return t ? (int)t->levels.size() : B200QR_EINVAL; }
+
+// Factor the m x n matrix dA (column-major, ldm) in place (leaf reflectors) and write the n x n
+// upper-triangular R (column-major, leading dimension n) to dR.  Asynchronous on `stream`.
+int b200qr_tsqr_factor(b200qr_tsqr_t t, float *dA, long long ldm, float *dR, void *stream_)
+{
+    if (!t || !dA || !dR || ldm < t->m || (ldm & 3) || ldm > 0x7fffffffLL) return B200QR_EINVAL;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int n = t->n, q = n / TB, fanin = t->fanin;
+    long long count = t->m / t->leaf_rows;
+    int rc = batched_launch(dA, t->leaf_rows, n, (int)ldm, t->leaf_rows, (int)count, t->d_leaf_tau, t->d_counter, stream);
+    if (rc != B200QR_OK) return rc;
+    const float *src = dA;
+    long long src_stride = t->leaf_rows;
+    int src_ld = (int)ldm;
+    for (auto &L : t->levels) {
+        const int sld = (int)(L.count * n);
+        gather_r_kernel<<<1024, 256, 0, stream>>>(src, src_stride, src_ld, n, (int)L.count, L.stack);
+        CKB(cudaGetLastError());
+        if (L.nfull > 0) {
+            rc = batched_launch(L.stack, fanin * n, n, sld, (long long)fanin * n, L.nfull, L.tau, t->d_counter, stream);
+            if (rc != B200QR_OK) return rc;
+        }
+        if (L.rest >= 2) {
+            rc = batched_launch(L.stack + (size_t)L.nfull * fanin * n, L.rest * n, n, sld, 0, 1,
+                                L.tau + (size_t)L.nfull * q * fanin * n, t->d_counter, stream);
+            if (rc != B200QR_OK) return rc;
+        }
+        src = L.stack; src_stride = (long long)fanin * n; src_ld = sld;
+    }
+    gather_r_kernel<<<64, 256, 0, stream>>>(src, 0, src_ld, n, 1, dR);       // top n x n, lower triangle zeroed
+    CKB(cudaGetLastError());
+    return B200QR_OK;
+}
+
+}  // extern "C"

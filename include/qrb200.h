@@ -136,6 +136,28 @@ int    b200qr_dist_factor(b200qr_dist_t d, void *stream);
 int    b200qr_dist_connect_local(b200qr_dist_t *all, int world);
 int    b200qr_dist_factor_group(b200qr_dist_t *all, int world, void *stream);
 
+/* ---- batched small problems and TSQR (BASELINE configs[2], configs[3]) ---------------------------
+ * nprob independent m x n problems with n <= 256 (at most 8 tile columns), problem b at
+ * dA + b*strideA, each factored in place exactly like cudaQRTask would factor it (same tile
+ * algorithm and output layout).  dTau receives nprob * K*p*32 floats (compact tau per problem,
+ * [(k*p + i)*32 + r]); dCounter is one int of device scratch.  Asynchronous on `stream`.       */
+int b200qr_batched_workspace_floats(int m, int n, int nprob, long long *tau_floats);
+int b200qr_batched_factor(float *dA, int m, int n, int ldm, long long strideA, int nprob, float *dTau, int *dCounter,
+                          void *stream);
+int b200qr_batched_last_cuda_error(void);
+/* Tall-skinny QR by a reduction tree: rows cut into leaves of leaf_rows (m % leaf_rows == 0), every
+ * leaf factored as one batched problem, the R factors stacked and reduced `fanin` at a time until
+ * one n x n R is left.  The reference handles a tall panel as one serial TSQRT chain
+ * (gridscheduler.c:136-154); the tree changes the Householder-vector layout (leaf reflectors stay in
+ * dA, inner nodes in the plan), so parity for this path is on R up to row signs.  For several
+ * GPUs: one plan per row block, all-gather the R factors, stack them and call
+ * b200qr_batched_factor once more (see bench.py / tests).                                       */
+typedef struct b200qr_tsqr_s *b200qr_tsqr_t;
+int b200qr_tsqr_create(b200qr_tsqr_t *t, long long m, int n, int leaf_rows, int fanin);
+int b200qr_tsqr_destroy(b200qr_tsqr_t t);
+int b200qr_tsqr_levels(b200qr_tsqr_t t);
+int b200qr_tsqr_factor(b200qr_tsqr_t t, float *dA, long long ldm, float *dR, void *stream);
+
 /* ---- trace of the device scheduler (opts.trace = 1) -------------------------------
  * For every tile task (k, i, j) the kernel records a global sequence number when the
  * task starts reading its inputs and when its outputs are published.  Records come

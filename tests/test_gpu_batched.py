@@ -1,0 +1,83 @@
+"""Batched small QR (BASELINE configs[2]) and TSQR (configs[3]) against the oracle / float64 LAPACK."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def batched(qr, torch, mats, m, n):
+    """mats: (nprob, n, m) float32 (each problem column-major m x n, ld = m); returns (out, tau_compact)."""
+    nprob = mats.shape[0]
+    d = torch.from_numpy(np.ascontiguousarray(mats)).cuda()
+    fl = C.c_longlong(0)
+    qr.check(qr.lib().b200qr_batched_workspace_floats(m, n, nprob, C.byref(fl)))
+    tau = torch.zeros(fl.value, dtype=torch.float32, device="cuda")
+    ctr = torch.zeros(1, dtype=torch.int32, device="cuda")
+    qr.check(qr.lib().b200qr_batched_factor(C.c_void_p(d.data_ptr()), m, n, m, m * n, nprob, C.c_void_p(tau.data_ptr()),
+                                            C.c_void_p(ctr.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    return d.cpu().numpy(), tau.cpu().numpy()
+
+
+def expand_tau(tc, m, n):
+    p, q = m // 32, n // 32
+    K = min(p, q)
+    t = tc.reshape(K, p, 32)
+    out = np.zeros((n, m), dtype=np.float32)
+    for k in range(K):
+        for i in range(k, p):
+            out[k * 32, i * 32:(i + 1) * 32] = t[k, i]
+    return out
+
+
+@pytest.mark.parametrize("m,n,nprob", [(256, 256, 5), (32, 32, 3), (64, 256, 2), (512, 128, 4), (2048, 256, 2)])
+def test_batched_matches_oracle_per_problem(cuda, qr, po, m, n, nprob):
+    mats = np.stack([po.randzo(m, n, seed=5 + b) for b in range(nprob)])
+    out, tau = batched(qr, cuda, mats, m, n)
+    per = tau.size // nprob
+    for b in range(nprob):
+        ref_out, ref_tau = po.tiled_qr(mats[b], m, n)
+        scale = max(1.0, float(np.max(np.abs(ref_out))))
+        assert np.max(np.abs(out[b] - ref_out)) <= 1e-4 * scale
+        assert np.max(np.abs(expand_tau(tau[b * per:(b + 1) * per], m, n) - ref_tau)) <= 1e-5 * max(1, n // 32)
+
+
+def test_batched_equals_single_matrix_path(cuda, qr, po):
+    """A 256x256 problem of the batch is bit-identical to b200qr_factor_device on that matrix."""
+    torch = cuda
+    m = n = 256
+    mats = np.stack([po.randzo(m, n, seed=9 + b) for b in range(300)])       # more problems than CTAs
+    out, _ = batched(qr, torch, mats, m, n)
+    plan = qr.Plan(m, n)
+    for b in (0, 7, 299):
+        d = torch.from_numpy(mats[b]).cuda()
+        plan.factor(d.data_ptr(), m, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(out[b], d.cpu().numpy())
+    plan.close()
+
+
+@pytest.mark.parametrize("m,n,leaf,fanin", [(4096, 256, 512, 2), (8192, 128, 256, 4), (12288, 256, 2048, 4), (2048, 64, 2048, 2),
+                                              (5120, 256, 512, 4)])
+def test_tsqr_r_factor(cuda, qr, m, n, leaf, fanin):
+    torch = cuda
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.rand((n, m), generator=g, device="cuda", dtype=torch.float32) * 2 - 1    # column-major m x n
+    d = A.clone()
+    h = C.c_void_p()
+    qr.check(qr.lib().b200qr_tsqr_create(C.byref(h), m, n, leaf, fanin))
+    R = torch.zeros((n, n), dtype=torch.float32, device="cuda")
+    qr.check(qr.lib().b200qr_tsqr_factor(h, C.c_void_p(d.data_ptr()), m, C.c_void_p(R.data_ptr()),
+                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    qr.lib().b200qr_tsqr_destroy(h)
+    Rm = R.t().double()                                  # (n, n) values, upper triangular
+    assert torch.count_nonzero(torch.tril(Rm, -1)) == 0
+    Ad = A.t().double()
+    G = Ad.t() @ Ad
+    assert (torch.linalg.norm(Rm.t() @ Rm - G) / torch.linalg.norm(G)).item() <= 50 * float(np.finfo(np.float32).eps)
+    R64 = torch.linalg.qr(Ad, mode="r").R
+    s = torch.sign(torch.diagonal(R64)) * torch.sign(torch.diagonal(Rm))
+    assert (torch.max(torch.abs(Rm - s[:, None] * R64)) / torch.max(torch.abs(R64))).item() <= 1e-4
