@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(288) panel_probe_kernel(const float *tile_in, 
     __shared__ __align__(16) float Rs[TB * 33];
     __shared__ __align__(16) float xs[2 * TB];
     __shared__ __align__(16) float ts[TB * TB];
+    __shared__ __align__(16) float ts2[TB * TB];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0) {
         float a[TB], b[TB];
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(288) panel_probe_kernel(const float *tile_in, 
         __syncwarp();
         for (int r = 0; r < reps; ++r) {
             load_col_smem(b, ts + lane * TB);
-            acc += tsqrt_warp(b, Rs, xs, lane);
+            acc += tsqrt_warp_v<false>(b, Rs, xs, ts2, lane);
         }
         long long t2 = clock64();
         store_col_gmem(tile_out + lane * TB, b);

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(BQ * 32, 2) batched_tiledqr_kernel(const Batch
                 if (lane == 0) panel_prog[k] = 1;
                 for (int i = k + 1; i < p; ++i) {
                     load_col_gmem(x, tile(i, k));
-                    float ti = tsqrt_warp(x, Vs, xs, lane);
+                    float ti = tsqrt_warp(x, Vs, xs, top, lane);
                     store_col_gmem(tile(i, k), x);
                     tb[((size_t)k * p + i) * TB + lane] = ti;
                     __threadfence_block();

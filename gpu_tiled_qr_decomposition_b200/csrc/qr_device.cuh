@@ -194,13 +194,16 @@ struct HouseScalars { float inv, tau; };
 __device__ __forceinline__ HouseScalars house_scalars(float x0, float ssq)
 {
     const float nsq = fmaf(x0, x0, ssq);
-    float rn = rsqrtf(nsq);
+    float rn, r0;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rn) : "f"(nsq));
     rn = rn * fmaf(-0.5f * nsq * rn, rn, 1.5f);            // one Newton step: ~1 ulp
     const float nrm = nsq * rn;
     const float piv = x0 + (x0 >= 0.f ? nrm : -nrm);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(piv));
+    r0 = fmaf(r0, fmaf(-piv, r0, 1.0f), r0);               // one Newton step
     HouseScalars h;
-    const bool degenerate = !(nsq > 0.f);
-    h.inv = degenerate ? 1.0f : __frcp_rn(piv);
+    const bool degenerate = !(nsq > 1e-36f);               // zero (or flushed) column: v stays unscaled, tau = 2
+    h.inv = degenerate ? 1.0f : r0;
     h.tau = degenerate ? 2.0f : fmaf(fabsf(x0), rn, 1.0f);
     return h;
 }
@@ -267,18 +270,25 @@ __device__ __forceinline__ float geqrt_warp(float (&a)[TB], float *xs, int lane)
 struct NoMid { __device__ __forceinline__ void operator()() const {} };
 // `mid` runs once, a quarter of the way through the tile: the persistent kernel uses it to publish
 // the PREVIOUS tile of the chain (whose TMA store has long completed by then) off the critical path.
-template <class Mid = NoMid>
-__device__ __forceinline__ float tsqrt_warp(float (&b)[TB], float *Rs, float *xs, int lane, Mid mid = Mid())
+// The reflector block V2 is assembled in the shared-memory tile `vout` (lane r writes V2(r,c) at
+// step c, one multiply per lane instead of 32 by the owner lane): element (r,c) at vout[c*32 + r],
+// or in the 128B-swizzled TMA layout when SWZ.  b[] is clobbered.
+template <bool SWZ, class Mid = NoMid>
+__device__ __forceinline__ float tsqrt_warp_v(float (&b)[TB], float *Rs, float *xs, float *vout, int lane, Mid mid = Mid())
 {
     float my_tau = 0.f;
     float ssq = dot32(b, b);
+    float *vdst = SWZ ? reinterpret_cast<float *>(reinterpret_cast<char *>(vout) + (lane & 3) * 4)
+                      : vout + lane;
 #pragma unroll 1
     for (int c = 0; c < TB; ++c) {
         if (c == 8) mid();
         const float rc = Rs[c * 33 + lane];                   // R(c, lane)
+        const float diag = Rs[c * 33 + c];                    // R(c, c): broadcast read
+        float *slot = xs + (c & 1) * TB;
         float x[TB];
-        bcast_col(x, b, xs + (c & 1) * TB, lane == c);        // x = B(:, c)
-        const HouseScalars h = house_scalars(__shfl_sync(FULL, rc, c), __shfl_sync(FULL, ssq, c));
+        bcast_col(x, b, slot, lane == c);                     // x = B(:, c)
+        const HouseScalars h = house_scalars(diag, __shfl_sync(FULL, ssq, c));
         // beta = tau (R(c,j) + v' B(:,j)),  v = x / piv
         const float beta = (lane >= c) ? h.tau * fmaf(h.inv, dot32(b, x), rc) : 0.f;
         Rs[c * 33 + lane] = rc - beta;
@@ -286,13 +296,22 @@ __device__ __forceinline__ float tsqrt_warp(float (&b)[TB], float *Rs, float *xs
 #pragma unroll
         for (int r = 0; r < TB; ++r) b[r] = fmaf(g, x[r], b[r]);
         ssq = dot32(b, b);                                    // needed from lane c+1 next step
-        if (lane == c) {
-#pragma unroll
-            for (int r = 0; r < TB; ++r) b[r] = x[r] * h.inv;
-            my_tau = h.tau;
-        }
+        const float vr = slot[lane] * h.inv;                  // V2(lane, c)
+        if (SWZ) *reinterpret_cast<float *>(reinterpret_cast<char *>(vdst) + c * 128 + ((((lane >> 2) ^ (c & 7))) << 4)) = vr;
+        else vdst[c * TB] = vr;
+        if (lane == c) my_tau = h.tau;
     }
+    __syncwarp();
     return my_tau;
+}
+// register-output flavour (single-tile kernels, batched kernel): V2 comes back in b[]
+template <class Mid = NoMid>
+__device__ __forceinline__ float tsqrt_warp(float (&b)[TB], float *Rs, float *xs, float *vtmp, int lane, Mid mid = Mid())
+{
+    const float t = tsqrt_warp_v<false>(b, Rs, xs, vtmp, lane, mid);
+    load_col_smem(b, vtmp + lane * TB);
+    __syncwarp();
+    return t;
 }
 
 // ------------------------------------------------------------------ a3/a4: UNMQR / TSMQR

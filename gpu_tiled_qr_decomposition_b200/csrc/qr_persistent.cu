@@ -84,7 +84,7 @@ struct Cfg {
     // per panel warp: 2 input tiles, 1 output tile, R (33-float rows) + broadcast slots.  The NC = 2
     // variant only runs role-split (a CTA is either a panel CTA or a sweep CTA), so its panel region
     // overlays the sweep stages; NC = 1 keeps them apart and can run both roles in one CTA.
-    static constexpr int PANEL_BYTES = 3 * TILE_BYTES + 5120;
+    static constexpr int PANEL_BYTES = 4 * TILE_BYTES + 5120;
     static constexpr int OFF_PANEL = NC == 2 ? 0 : SWEEP_END;
     static constexpr int OFF_BAR = NC == 2 ? SWEEP_END : SWEEP_END + NPW * PANEL_BYTES;
     static constexpr int SMEM_BYTES = OFF_BAR + 256;
@@ -170,9 +170,9 @@ __device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int p
     const int p = P.p;
     unsigned char *mine = g_smem + C::OFF_PANEL + pw * C::PANEL_BYTES;
     float *pin0 = reinterpret_cast<float *>(mine);                      // 2 input slots, TB*TB floats apart
-    float *pout = reinterpret_cast<float *>(mine + 2 * TILE_BYTES);
-    float *Rs = reinterpret_cast<float *>(mine + 3 * TILE_BYTES);
-    float *xs = reinterpret_cast<float *>(mine + 3 * TILE_BYTES + 4352);   // 2 x 128 B broadcast slots
+    float *pout0 = reinterpret_cast<float *>(mine + 2 * TILE_BYTES);   // 2 output slots (tile row parity)
+    float *Rs = reinterpret_cast<float *>(mine + 4 * TILE_BYTES);
+    float *xs = reinterpret_cast<float *>(mine + 4 * TILE_BYTES + 4352);   // 2 x 128 B broadcast slots
     uint64_t *pfull = reinterpret_cast<uint64_t *>(g_smem + C::OFF_BAR) + 3 * C::NS + 2 * pw;
     int *prog_col = P.prog + (size_t)k * p;
     float *tauc = P.tauc + (size_t)k * p * TB;
@@ -196,6 +196,7 @@ __device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int p
         }
     };
     auto store_tile = [&](int row, const float (&x)[TB]) {   // x -> pout -> TMA store (async)
+        float *pout = pout0 + (row & 1) * TB * TB;
         store_col_sw(pout, lane, x);
         fence_proxy_async_smem();
         __syncwarp();                                // also orders this warp's tau stores before lane 0's release
@@ -232,11 +233,17 @@ __device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int p
         float b[TB];
         load_col_sw(b, pin0 + s * TB * TB, lane);
         if (lane == 0) trace_mark(P, k, i, k, 0);
-        float ti = tsqrt_warp(b, Rs, xs, lane, publish);         // publishes the previous tile on the way
+        // V2 is assembled straight in a TMA output tile (two of them, alternating by row: the store
+        // of the previous tile is still in flight and is published a quarter of the way through)
+        float *pout = pout0 + (i & 1) * TB * TB;
+        float ti = tsqrt_warp_v<true>(b, Rs, xs, pout, lane, publish);
         if (lane == 0) trace_mark(P, k, i, k, 1);
         publish();
         tauc[i * TB + lane] = ti;
-        store_tile(i, b);
+        fence_proxy_async_smem();
+        __syncwarp();                                // also orders this warp's tau stores before lane 0's release
+        if (lane == 0) { tma_store_2d(mapA, i * TB, k * TB, pout); bulk_commit(); }
+        pending = i;
         have_cur = have_next;
     }
     publish();
@@ -244,10 +251,10 @@ __device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int p
     float f[TB];
 #pragma unroll
     for (int r = 0; r < TB; ++r) f[r] = Rs[r * 33 + lane];
-    store_col_sw(pout, lane, f);
+    store_col_sw(pout0, lane, f);
     fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0) { tma_store_2d(mapA, k * TB, k * TB, pout); bulk_commit(); bulk_wait_all(); }
+    if (lane == 0) { tma_store_2d(mapA, k * TB, k * TB, pout0); bulk_commit(); bulk_wait_all(); }
     __syncwarp();
 }
 
@@ -502,7 +509,7 @@ __device__ void tile_task_device(int type, int l, int m, int k, float *mat, floa
         for (int r = 0; r < TB; ++r) Rs[r * 33 + lane] = x[r];
         __syncwarp();
         load_col_gmem(x, tile(mat, l, k));
-        float t = tsqrt_warp(x, Rs, xs, lane);
+        float t = tsqrt_warp(x, Rs, xs, top, lane);
         store_col_gmem(tile(mat, l, k), x);
         float *rcol = tile(mat, k, k);
 #pragma unroll
