@@ -242,7 +242,7 @@ def run_b200_single(args):
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "GFLOP/s", "h2d_bytes_per_step": 4 * n * n,
                     "d2h_bytes_per_step": 4 * n * n, "api": "cudaQRTask(host float*, m, n, ldm, maxblocks) on pinned "
-                    "host memory; includes plan/workspace allocation", "steps": e2e_steps,
+                    "host memory (workspace cached between calls of one shape)", "steps": e2e_steps,
                     "max_abs_diff_vs_device_path": e2e_err},
             "gpu_launches": args.steps * 1, "clocks": clocks, "check": {"gram_rel_err": gram}}
     print(json.dumps(line), flush=True)

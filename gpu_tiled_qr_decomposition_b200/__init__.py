@@ -31,7 +31,7 @@ EXPORTS = (
     "b200qr_dist_connect_local", "b200qr_dist_factor_group",
     "b200qr_batched_workspace_floats", "b200qr_batched_factor", "b200qr_batched_last_cuda_error",
     "b200qr_tsqr_create", "b200qr_tsqr_destroy", "b200qr_tsqr_levels", "b200qr_tsqr_factor",
-    "cudaQRTask", "cudaQRFull", "testDAPP", "doCUDADAPP",
+    "b200qr_apply_q", "b200qr_release_cache", "cudaQRTask", "cudaQRFull", "testDAPP", "doCUDADAPP",
 )
 
 
@@ -128,6 +128,8 @@ def lib():
         L.b200qr_tsqr_destroy.argtypes = [vp]
         L.b200qr_tsqr_levels.argtypes = [vp]
         L.b200qr_tsqr_factor.argtypes = [vp, vp, C.c_longlong, vp, vp]
+        L.b200qr_release_cache.restype = None
+        L.b200qr_apply_q.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp]
         L.cudaQRTask.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
         L.cudaQRTask.restype = None
         L.cudaQRFull.argtypes = [vp, C.c_int, C.c_int]
@@ -177,6 +179,15 @@ class Plan:
     def tau_to_reference(self, dptr, ldtau, stream=0):
         check(lib().b200qr_tau_to_reference(self._h, C.c_void_p(dptr), ldtau, C.c_void_p(stream)),
               "b200qr_tau_to_reference")
+
+    @property
+    def tau_ptr(self):
+        return lib().b200qr_plan_tau_device(self._h)
+
+    def apply_q(self, dA_ptr, ldm, dC_ptr, ldc, ncols, transpose, stream=0):
+        """C <- Q^T C (transpose) or Q C with the reflectors of the matrix this plan just factored."""
+        check(lib().b200qr_apply_q(C.c_void_p(dA_ptr), self.m, self.n, ldm, C.c_void_p(self.tau_ptr), C.c_void_p(dC_ptr),
+                                   ldc, ncols, int(transpose), C.c_void_p(stream)), "b200qr_apply_q")
 
     def read_trace(self):
         import numpy as np

@@ -132,6 +132,91 @@ __global__ void gather_r_kernel(const float *src, long long strideA, int ldm, in
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Apply Q or Q^T of a factored matrix (tile layout of cudaQRTask / b200qr_factor_device) to C.
+// The reference never forms or applies Q; this replays the flat tree:
+//   Q^T C:  for k = 0..K-1:  GEQRT reflectors of tile (k,k) on C tile row k, then for l = k+1..p-1
+//           the TSQRT reflectors of tile (l,k) on C tile rows (k, l)       (reflector 0 first);
+//   Q C:    the same blocks in reverse order, reflectors of a block last-to-first.
+// One warp owns 32 columns of C (a thread = one column), C tile row k resident in shared memory.
+template <bool FWD>    // FWD = true: Q^T C
+__device__ __forceinline__ void apply_block(float (&x)[TB], float *top, int top_rs, const float *vs, const float *ts,
+                                            bool diag)
+{
+    if constexpr (FWD) {
+        if (diag) apply_reflectors_nc<1, false>(x, x, nullptr, nullptr, 0, vs, ts);
+        else apply_reflectors_nc<1, true>(x, x, top, top, top_rs, vs, ts);
+    } else {
+#pragma unroll 2
+    for (int c = TB - 1; c >= 0; --c) {
+        float v[TB];
+        load_col_smem(v, vs + c * TB);
+        if (diag) {
+#pragma unroll
+            for (int r = 0; r < TB; ++r) v[r] = (r > c) ? v[r] : ((r == c) ? 1.0f : 0.f);
+        }
+        const float a0 = diag ? 0.f : top[c * top_rs];
+        const float beta = ts[c] * (a0 + dot32(x, v));
+        if (!diag) top[c * top_rs] = a0 - beta;
+#pragma unroll
+        for (int r = 0; r < TB; ++r) x[r] = fmaf(-beta, v[r], x[r]);
+    }
+    }
+}
+
+template <bool FWD>
+__global__ void __launch_bounds__(128) apply_q_kernel(const float *A, int ldm, const float *tauc, int p, int K, float *Cm,
+                                                      int ldc, int ncols)
+{
+    __shared__ __align__(16) float sm[4][1024 + 1024 + 32];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int col = (blockIdx.x * 4 + w) * TB + lane;
+    if ((blockIdx.x * 4 + w) * TB >= ncols) return;
+    float *Vs = sm[w], *top = Vs + 1024, *ts = top + 1024;
+    float *ccol = Cm + (size_t)col * ldc;
+    float x[TB];
+    auto load_v = [&](int I, int J) {
+        load_col_gmem(x, A + (size_t)(J * TB + lane) * ldm + I * TB);
+        store_col_smem(Vs + lane * TB, x);
+        ts[lane] = __ldcg(tauc + ((size_t)J * p + I) * TB + lane);
+        __syncwarp();
+    };
+    for (int kk = 0; kk < K; ++kk) {
+        const int k = FWD ? kk : K - 1 - kk;
+        // C tile row k resident
+        load_col_gmem(x, ccol + k * TB);
+        if (FWD) {
+            load_v(k, k);
+            load_col_gmem(x, ccol + k * TB);
+            apply_block<true>(x, nullptr, 0, Vs, ts, true);
+        }
+#pragma unroll
+        for (int r = 0; r < TB; ++r) top[r * TB + lane] = x[r];
+        __syncwarp();
+        for (int ll = k + 1; ll < p; ++ll) {
+            const int l = FWD ? ll : p - 1 - (ll - k - 1);
+            load_v(l, k);
+            load_col_gmem(x, ccol + l * TB);
+            apply_block<FWD>(x, top + lane, TB, Vs, ts, false);
+            store_col_gmem(ccol + l * TB, x);
+            __syncwarp();
+        }
+#pragma unroll
+        for (int r = 0; r < TB; ++r) x[r] = top[r * TB + lane];
+        if (!FWD) {
+            float keep[TB];
+#pragma unroll
+            for (int r = 0; r < TB; ++r) keep[r] = x[r];
+            load_v(k, k);                       // clobbers x
+            apply_block<false>(keep, nullptr, 0, Vs, ts, true);
+#pragma unroll
+            for (int r = 0; r < TB; ++r) x[r] = keep[r];
+        }
+        store_col_gmem(ccol + k * TB, x);
+        __syncwarp();
+    }
+}
+
 }  // namespace qrb200
 
 using namespace qrb200;
@@ -197,6 +282,23 @@ int b200qr_batched_factor(float *dA, int m, int n, int ldm, long long strideA, i
 }
 
 int b200qr_batched_last_cuda_error(void) { return g_batched_cuda; }
+
+// C <- Q^T C (transpose != 0) or Q C, for the Q of a matrix factored by cudaQRTask /
+// b200qr_factor_device / b200qr_batched_factor: dA = factored m x n matrix (ldm), dTauCompact =
+// [(k*p + i)*32 + r] (b200qr_plan_tau_device), dC = m x ncols (ldc), ncols % 32 == 0.
+int b200qr_apply_q(const float *dA, int m, int n, int ldm, const float *dTauCompact, float *dC, int ldc, int ncols,
+                   int transpose, void *stream)
+{
+    if (!dA || !dTauCompact || !dC || m <= 0 || n <= 0 || m % TB || n % TB || ncols <= 0 || ncols % TB || ldm < m ||
+        ldc < m || (ldm & 3) || (ldc & 3))
+        return B200QR_EINVAL;
+    const int p = m / TB, q = n / TB, K = p < q ? p : q;
+    const int blocks = (ncols / TB + 3) / 4;
+    if (transpose) apply_q_kernel<true><<<blocks, 128, 0, (cudaStream_t)stream>>>(dA, ldm, dTauCompact, p, K, dC, ldc, ncols);
+    else apply_q_kernel<false><<<blocks, 128, 0, (cudaStream_t)stream>>>(dA, ldm, dTauCompact, p, K, dC, ldc, ncols);
+    CKB(cudaGetLastError());
+    return B200QR_OK;
+}
 
 // ---- TSQR ------------------------------------------------------------------------------------
 // Level structure: `count` R factors (n x n) are stacked into a (count*n) x n matrix and factored in

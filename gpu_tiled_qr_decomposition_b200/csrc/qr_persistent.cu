@@ -1109,6 +1109,23 @@ int b200qr_tile_task(int type, int l, int m, int k, float *dMat, float *dTauMat,
 // ---------------------------------------------------------------- legacy entry points
 // (reference include/gpucalc.h:3-6)
 
+struct LegacyCache {
+    b200qr_plan_t plan = nullptr;
+    float *dA = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int m = 0, n = 0, grid_ctas = 0, dev = -1;
+};
+static LegacyCache g_cache;
+
+void b200qr_release_cache(void)
+{
+    if (g_cache.plan) b200qr_plan_destroy(g_cache.plan);
+    if (g_cache.dA) cudaFree(g_cache.dA);
+    if (g_cache.e0) cudaEventDestroy(g_cache.e0);
+    if (g_cache.e1) cudaEventDestroy(g_cache.e1);
+    g_cache = LegacyCache();
+}
+
 static bool env_on(const char *name)
 {
     const char *v = getenv(name);
@@ -1127,38 +1144,44 @@ void cudaQRTask(float *mat, int m, int n, int ldm, int maxblocks)
     for (int k = 0; k < (p < q ? p : q); ++k) total += (long)(p - k) * (q - k);
     if (!quiet) printf("(%d,%d)\n%ld tasks\n", m, n, total);   // calcTotalTasks, gpucalc.cu:1557
 
+    // The reference allocates and frees its workspace on every call (gpucalc.cu:1601-1612,
+    // 1672-1676).  Here the plan and the device copy of the matrix are kept between calls of the
+    // same shape (like the reference, this entry point is not thread-safe): the second call of a
+    // loop pays for the copies and the kernel only.  b200qr_release_cache() / QRB200_COMPAT_RESET drop it.
     b200qr_opts opts;
     memset(&opts, 0, sizeof opts);
     if (env_on("QRB200_HONOR_MAXBLOCKS") && maxblocks > 0) opts.grid_ctas = maxblocks;
-    b200qr_plan_t pl = nullptr;
-    float *dA = nullptr;
-    cudaEvent_t e0, e1;
-    int rc = b200qr_plan_create(&pl, m, n, &opts);
-    if (rc) { printf("error creating plan: %s\n", b200qr_strerror(rc)); return; }
-    if (cudaMalloc(&dA, sizeof(float) * (size_t)m * n) != cudaSuccess) {
-        printf("error allocating dev mat\n");
-        b200qr_plan_destroy(pl);
-        return;
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (g_cache.plan && (g_cache.m != m || g_cache.n != n || g_cache.grid_ctas != opts.grid_ctas || g_cache.dev != dev))
+        b200qr_release_cache();
+    if (!g_cache.plan) {
+        int rc = b200qr_plan_create(&g_cache.plan, m, n, &opts);
+        if (rc) { printf("error creating plan: %s\n", b200qr_strerror(rc)); g_cache.plan = nullptr; return; }
+        if (cudaMalloc(&g_cache.dA, sizeof(float) * (size_t)m * n) != cudaSuccess) {
+            printf("error allocating dev mat\n");
+            b200qr_release_cache();
+            return;
+        }
+        cudaEventCreate(&g_cache.e0); cudaEventCreate(&g_cache.e1);
+        g_cache.m = m; g_cache.n = n; g_cache.grid_ctas = opts.grid_ctas; g_cache.dev = dev;
     }
+    float *dA = g_cache.dA;
     if (cudaMemcpy2D(dA, sizeof(float) * m, mat, sizeof(float) * ldm, sizeof(float) * m, n,
                      cudaMemcpyHostToDevice) != cudaSuccess)
         printf("error cpying dev mat\n");
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventRecord(e0, 0);
-    rc = b200qr_factor_device(pl, dA, m, nullptr);
-    cudaEventRecord(e1, 0);
-    cudaError_t se = cudaEventSynchronize(e1);
+    cudaEventRecord(g_cache.e0, 0);
+    int rc = b200qr_factor_device(g_cache.plan, dA, m, nullptr);
+    cudaEventRecord(g_cache.e1, 0);
+    cudaError_t se = cudaEventSynchronize(g_cache.e1);
     if (rc || se != cudaSuccess) printf("error running QR kernel: %s (%d)\n", b200qr_strerror(rc), (int)se);
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventElapsedTime(&ms, g_cache.e0, g_cache.e1);
     if (!quiet) printf("GPU: %5.3f ms\n", ms);                 // gpucalc.cu:1647
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (cudaMemcpy2D(mat, sizeof(float) * ldm, dA, sizeof(float) * m, sizeof(float) * m, n,
                      cudaMemcpyDeviceToHost) != cudaSuccess)
         printf("copy back failed\n");
-    cudaFree(dA);
-    b200qr_plan_destroy(pl);
-    if (env_on("QRB200_COMPAT_RESET")) cudaDeviceReset();       // gpucalc.cu:1685
+    if (env_on("QRB200_COMPAT_RESET")) { b200qr_release_cache(); cudaDeviceReset(); }   // gpucalc.cu:1685
 }
 
 void cudaQRFull(float *mat, int m, int n)

@@ -17,7 +17,8 @@ extern "C" {
  * Householder vectors below.  Prints "(m,n)\n<T> tasks\n" and "GPU: <ms> ms\n" like the
  * reference unless QRB200_QUIET=1.  `maxblocks` capped the reference's persistent grid
  * at a Fermi-era co-residency limit; here the grid is sized from the device and
- * maxblocks is only honoured when QRB200_HONOR_MAXBLOCKS=1.  cudaDeviceReset() is only
+ * maxblocks is only honoured when QRB200_HONOR_MAXBLOCKS=1.  The workspace is kept between calls
+ * of the same shape (b200qr_release_cache() in qrb200.h frees it).  cudaDeviceReset() is only
  * issued when QRB200_COMPAT_RESET=1 (the reference always resets, gpucalc.cu:1685). */
 void cudaQRTask(float *mat, int m, int n, int ldm, int maxblocks);
 

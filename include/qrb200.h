@@ -158,6 +158,16 @@ int b200qr_tsqr_destroy(b200qr_tsqr_t t);
 int b200qr_tsqr_levels(b200qr_tsqr_t t);
 int b200qr_tsqr_factor(b200qr_tsqr_t t, float *dA, long long ldm, float *dR, void *stream);
 
+/* ---- apply Q (the reference has no such routine, qrdecomp.c:1292 multAB is unused) ---
+ * C <- Q^T C (transpose != 0) or Q C for the Q held implicitly by a factored matrix: dA = factored
+ * m x n matrix (ldm), dTauCompact = [(k*p + i)*32 + r] (b200qr_plan_tau_device), dC = m x ncols
+ * column-major (ldc), ncols % 32 == 0.  Asynchronous on `stream`.                               */
+int b200qr_apply_q(const float *dA, int m, int n, int ldm, const float *dTauCompact, float *dC, int ldc, int ncols,
+                   int transpose, void *stream);
+
+/* cudaQRTask keeps its plan and device buffer between calls of the same shape; this frees them. */
+void b200qr_release_cache(void);
+
 /* ---- trace of the device scheduler (opts.trace = 1) -------------------------------
  * For every tile task (k, i, j) the kernel records a global sequence number when the
  * task starts reading its inputs and when its outputs are published.  Records come
