@@ -27,7 +27,7 @@ EXPORTS = (
     "b200qr_sched_predecessors", "b200qr_sched_device_order", "b200qr_sched_sweep_order", "b200qr_sched_rank_tickets",
     "b200qr_dist_create", "b200qr_dist_destroy", "b200qr_dist_handle_bytes", "b200qr_dist_export",
     "b200qr_dist_connect", "b200qr_dist_matrix", "b200qr_dist_tau_device", "b200qr_dist_block",
-    "b200qr_dist_owner", "b200qr_dist_grid", "b200qr_dist_reset", "b200qr_dist_factor",
+    "b200qr_dist_owner", "b200qr_dist_grid", "b200qr_dist_read_trace", "b200qr_dist_tile_tasks", "b200qr_dist_reset", "b200qr_dist_factor",
     "b200qr_dist_connect_local", "b200qr_dist_factor_group",
     "b200qr_batched_workspace_floats", "b200qr_batched_factor", "b200qr_batched_last_cuda_error",
     "b200qr_tsqr_create", "b200qr_tsqr_destroy", "b200qr_tsqr_levels", "b200qr_tsqr_factor",
@@ -119,6 +119,9 @@ def lib():
         L.b200qr_dist_owner.argtypes = [vp, C.c_int]
         L.b200qr_dist_grid.argtypes = [vp]
         L.b200qr_dist_reset.argtypes = [vp, vp]
+        L.b200qr_dist_read_trace.argtypes = [vp, vp, C.c_long]
+        L.b200qr_dist_tile_tasks.argtypes = [vp]
+        L.b200qr_dist_tile_tasks.restype = C.c_long
         L.b200qr_dist_factor.argtypes = [vp, vp]
         L.b200qr_dist_connect_local.argtypes = [C.POINTER(vp), C.c_int]
         L.b200qr_dist_factor_group.argtypes = [C.POINTER(vp), C.c_int, vp]
@@ -248,11 +251,11 @@ def device_order(M, N):
 class DistRank:
     """One rank of the 1-D block-cyclic multi-GPU factorisation (b200qr_dist_*)."""
 
-    def __init__(self, m, n, rank, world, share_device=0, grid_ctas=0):
+    def __init__(self, m, n, rank, world, share_device=0, grid_ctas=0, trace=0):
         self.m, self.n, self.rank, self.world = m, n, rank, world
         self._h = C.c_void_p()
         o = Opts()
-        o.grid_ctas, o.share_device = int(grid_ctas), int(share_device)
+        o.grid_ctas, o.share_device, o.trace = int(grid_ctas), int(share_device), int(trace)
         check(lib().b200qr_dist_create(C.byref(self._h), m, n, rank, world, C.byref(o)), "b200qr_dist_create")
         self.block = lib().b200qr_dist_block(self._h)
 
@@ -295,6 +298,13 @@ class DistRank:
         """Compact tau [(k*p + i)*32 + r], K*p*32 floats."""
         p, K = self.m // TILE, min(self.m, self.n) // TILE
         check(lib().b200qr_copy(C.c_void_p(dst_ptr), C.c_void_p(self.tau_ptr), K * p * TILE * 4), "b200qr_copy")
+
+    def read_trace(self):
+        import numpy as np
+        n = lib().b200qr_dist_tile_tasks(self._h)
+        out = np.zeros((n, 6), dtype=np.int32)
+        check(lib().b200qr_dist_read_trace(self._h, out.ctypes.data_as(C.c_void_p), n), "b200qr_dist_read_trace")
+        return out
 
     def reset(self, stream=0):
         check(lib().b200qr_dist_reset(self._h, C.c_void_p(stream)), "b200qr_dist_reset")

@@ -188,9 +188,13 @@ __device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int p
     auto publish = [&]() {                           // wait for the store, fence, release the flag
         if (pending >= 0) {
             if (lane == 0) {
+                // The tile, its tau and this word all live in THIS GPU's memory, whose L2 is the point
+                // of coherence for local and NVLink readers alike: a gpu-scope fence orders them there.
+                // (A system-scope fence here costs ~13 us per tile on the chain's critical path; remote
+                // readers poll with ld.relaxed.sys and fence at system scope on their side.)
                 bulk_wait_all();
-                if (P.world > 1) { __threadfence_system(); st_release_sys(prog_col + pending, k + 1); }
-                else { __threadfence(); st_release(prog_col + pending, k + 1); }
+                __threadfence();
+                st_release(prog_col + pending, k + 1);
             }
             pending = -1;
         }
@@ -752,20 +756,26 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
 
     // Kernel variant and roles.  Large grids split the roles: a few CTAs run only TSQRT chains
     // (two panel warps each, undisturbed by the FFMA-bound consumers), the rest only sweeps with
-    // 2 matrix columns per consumer thread (16 tile columns per sweep).  The number of panel
-    // warps sets how many panel chains advance at once: about (chain work) / (sweep work per
-    // warp-time); measured on a B200 (13.7 us per TSQRT, 8.6 us per 16-tile sweep row) plus slack
-    // for the lock-step diagonal sweeps that is ~8000 / q panel chains.  Small grids (tests, tiny
-    // matrices) run both roles in every CTA with the 1-column variant.  With several ranks the
-    // variant must be the same everywhere (it fixes the distribution block), so it is derived
-    // from the shape and the world size only.
+    // 2 matrix columns per consumer thread (16 tile columns per sweep).  The number of panel CTAs
+    // balances the two streams with the costs measured on a B200 (tools/probe_panel.py,
+    // tools/trace_timeline.py): 8.7 us per TSQRT of a chain, 0.54 us of sweep-CTA time per trailing
+    // tile task.  The panel chains of consecutive steps live on ONE rank at a time (a block of 16
+    // tile columns), so the panel stream does not speed up with more ranks while each rank's sweep
+    // share shrinks: the split is world-aware.  Small grids (tests, tiny matrices) run both roles
+    // in every CTA with the 1-column variant.  With several ranks the variant must be the same
+    // everywhere (it fixes the distribution block), so it depends on shape and world size only.
     pl->nc = 1; pl->npanel_ctas = 0;
     const bool big = world > 1 ? q >= 32 * world : (grid >= 16 && q >= 32);
     if (big && grid >= 16) {
         pl->nc = 2;
-        int want = (8000 / q + 2 + NPW - 1) / NPW;
-        if (want < 2) want = 2;
-        if (want > grid / 5) want = grid / 5;
+        double ptiles = 0, stiles = 0;
+        for (int k = 0; k < K; ++k) { ptiles += p - k; stiles += (double)(p - k) * (q - k - 1); }
+        int want = 2;
+        for (; want < grid / 4; ++want) {
+            const double t_panel = ptiles * 8.7 / (NPW * want);
+            const double t_sweep = stiles * 0.54 / ((double)world * (grid - want));
+            if (t_panel <= 0.6 * t_sweep) break;
+        }
         pl->npanel_ctas = want;
     }
     if (world == 1) {
@@ -939,6 +949,10 @@ int b200qr_dist_block(b200qr_dist_t d) { return d ? d->plan.G : B200QR_EINVAL; }
 int b200qr_dist_owner(b200qr_dist_t d, int tile_col) { return d ? (tile_col / d->plan.G) % d->plan.world : B200QR_EINVAL; }
 int b200qr_dist_grid(b200qr_dist_t d) { return d ? d->plan.grid : B200QR_EINVAL; }
 const float *b200qr_dist_tau_device(b200qr_dist_t d) { return d ? d->plan.d_tauc : nullptr; }
+
+int b200qr_plan_read_trace(b200qr_plan_t pl, int *out6, long cap);
+int b200qr_dist_read_trace(b200qr_dist_t d, int *out6, long cap) { return d ? b200qr_plan_read_trace(&d->plan, out6, cap) : B200QR_EINVAL; }
+long b200qr_dist_tile_tasks(b200qr_dist_t d) { return d ? d->plan.tile_tasks : B200QR_EINVAL; }
 
 int b200qr_dist_export(b200qr_dist_t d, void *out_bytes)
 {
