@@ -354,14 +354,26 @@ __device__ __forceinline__ void apply_block_reflectors(float (&b)[TB], float *to
 // this thread's entries of the resident tile row (element c at top[c*top_rs]).
 // HAS_TOP = false takes the raw diagonal tile (R above the diagonal) and substitutes the
 // implied zeros / unit diagonal on the fly (UNMQR, qrdecomp.c:620-644).
-template <int NC, bool HAS_TOP>
+// VSWZ: vs is a tile in the 128B-swizzled TMA layout (the panel warp applies the block it has just
+// assembled in its output tile); otherwise dense, reflector c at vs[c*32 .. c*32+31].
+template <int NC, bool HAS_TOP, bool VSWZ = false>
 __device__ __forceinline__ void apply_reflectors_nc(float (&b0)[TB], float (&b1)[TB], float *top0, float *top1,
                                                     int top_rs, const float *vs, const float *ts)
 {
 #pragma unroll 2
     for (int c = 0; c < TB; ++c) {
         float v[TB];
-        load_col_smem(v, vs + c * TB);
+        if (VSWZ) {
+            const char *base = reinterpret_cast<const char *>(vs) + c * 128;
+            const int sw = (c & 7) << 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 t4 = *reinterpret_cast<const float4 *>(base + ((i << 4) ^ sw));
+                v[4 * i] = t4.x; v[4 * i + 1] = t4.y; v[4 * i + 2] = t4.z; v[4 * i + 3] = t4.w;
+            }
+        } else {
+            load_col_smem(v, vs + c * TB);
+        }
         if (!HAS_TOP) {
 #pragma unroll
             for (int r = 0; r < TB; ++r) v[r] = (r > c) ? v[r] : ((r == c) ? 1.0f : 0.f);

@@ -64,6 +64,7 @@ struct Params {
     const int *panel_tab;     // panel ticket -> k (the steps whose panel column this rank owns)
     int npanels;
     int rank, world;
+    int la_enable;            // panel warps also update the next panel's column (look-ahead)
     const int *peer_prog[MAXW];     // progress words of every rank ([rank] = prog)
     const float *peer_tauc[MAXW];   // compact tau of every rank ([rank] = tauc)
     int npanel_ctas;          // > 0: role split -- CTAs [0, npanel_ctas) run only panel warps, the rest only sweeps;
@@ -84,7 +85,7 @@ struct Cfg {
     // per panel warp: 2 input tiles, 1 output tile, R (33-float rows) + broadcast slots.  The NC = 2
     // variant only runs role-split (a CTA is either a panel CTA or a sweep CTA), so its panel region
     // overlays the sweep stages; NC = 1 keeps them apart and can run both roles in one CTA.
-    static constexpr int PANEL_BYTES = 4 * TILE_BYTES + 5120;
+    static constexpr int PANEL_BYTES = 8 * TILE_BYTES + 5120;      // in 2, out 2, R/scratch, top 1, look-ahead 3
     static constexpr int OFF_PANEL = NC == 2 ? 0 : SWEEP_END;
     static constexpr int OFF_BAR = NC == 2 ? SWEEP_END : SWEEP_END + NPW * PANEL_BYTES;
     static constexpr int SMEM_BYTES = OFF_BAR + 256;
@@ -161,6 +162,17 @@ __device__ __forceinline__ void trace_mark(const Params &P, int k, int i, int j,
             P.trace_mode == 2 ? (int)(unsigned)gtimer() : atomicAdd(&P.ctr[1], 1);
 }
 
+// Look-ahead: the panel warp of step k also applies the step to tile column k+1 -- the next panel's
+// column -- tile by tile right behind its own TSQRT, with the reflector block still in shared
+// memory.  The next panel then depends on this warp only (not on a sweep CTA's load / compute /
+// store / publish round trip), which shortens the lag between consecutive panels from ~75 us to
+// ~35 us; the sweeps skip that column.  Not done across a distribution-block boundary with several
+// ranks (column k+1 then lives on another GPU): there the ordinary sweep keeps the column.
+__device__ __forceinline__ bool lookahead(const Params &P, int k, int G)
+{
+    return P.la_enable && k + 1 < P.q && (P.world == 1 || (k + 1) % G != 0);
+}
+
 // ------------------------------------------------------------------ P(k): the panel warp
 template <int NC>
 __device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int pw, uint32_t &phbits, const Watch &wd)
@@ -173,43 +185,53 @@ __device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int p
     float *pout0 = reinterpret_cast<float *>(mine + 2 * TILE_BYTES);   // 2 output slots (tile row parity)
     float *Rs = reinterpret_cast<float *>(mine + 4 * TILE_BYTES);
     float *xs = reinterpret_cast<float *>(mine + 4 * TILE_BYTES + 4352);   // 2 x 128 B broadcast slots
+    float *ptau = reinterpret_cast<float *>(mine + 4 * TILE_BYTES + 4608); // tau of the current block
+    float *ptop = reinterpret_cast<float *>(mine + 4 * TILE_BYTES + 5120); // look-ahead: tile (k, k+1), [c][lane]
+    float *pla0 = reinterpret_cast<float *>(mine + 5 * TILE_BYTES + 5120); // look-ahead: 3 in/out slots
     uint64_t *pfull = reinterpret_cast<uint64_t *>(g_smem + C::OFF_BAR) + 3 * C::NS + 2 * pw;
     int *prog_col = P.prog + (size_t)k * p;
+    int *prog_la = P.prog + (size_t)(k + 1) * p;
     float *tauc = P.tauc + (size_t)k * p * TB;
+    const bool la = lookahead(P, k, C::G);
 
-    auto issue = [&](int row, int s) {               // TMA-load tile (row, k) into input slot s
+    auto ready = [&](int row) {
+        return ld_relaxed(prog_col + row) >= k && (!la || ld_relaxed(prog_la + row) >= k);
+    };
+    auto wait_ready = [&](int row) {
+        unsigned spins = 0;
+        while (!ready(row)) { __nanosleep(32); wd.check(spins); }
+        __threadfence();
+    };
+    auto issue = [&](int row, int s) {               // TMA-load tile (row, k) [and (row, k+1)] into slot s
         if (lane == 0) {
             fence_proxy_async();
-            mbar_arrive_expect_tx(&pfull[s], TILE_BYTES);
+            mbar_arrive_expect_tx(&pfull[s], la ? 2 * TILE_BYTES : TILE_BYTES);
             tma_load_2d(pin0 + s * TB * TB, mapA, row * TB, k * TB, &pfull[s]);
+            if (la) tma_load_2d(pla0 + ((row - k) % 3) * TB * TB, mapA, row * TB, (k + 1) * TB, &pfull[s]);
         }
     };
-    int pending = -1;                                // tile row whose store is in flight, unpublished
-    auto publish = [&]() {                           // wait for the store, fence, release the flag
+    int pending = -1;                                // tile row whose stores are in flight, unpublished
+    auto publish = [&]() {                           // wait for the stores, fence, release the flags
         if (pending >= 0) {
             if (lane == 0) {
-                // The tile, its tau and this word all live in THIS GPU's memory, whose L2 is the point
-                // of coherence for local and NVLink readers alike: a gpu-scope fence orders them there.
+                // The tiles, their tau and these words all live in THIS GPU's memory, whose L2 is the
+                // point of coherence for local and NVLink readers alike: a gpu-scope fence orders them.
                 // (A system-scope fence here costs ~13 us per tile on the chain's critical path; remote
                 // readers poll with ld.relaxed.sys and fence at system scope on their side.)
                 bulk_wait_all();
                 __threadfence();
                 st_release(prog_col + pending, k + 1);
+                if (la && pending > k) {
+                    trace_mark(P, k, pending, k + 1, 1);
+                    st_release(prog_la + pending, k + 1);
+                }
             }
             pending = -1;
         }
     };
-    auto store_tile = [&](int row, const float (&x)[TB]) {   // x -> pout -> TMA store (async)
-        float *pout = pout0 + (row & 1) * TB * TB;
-        store_col_sw(pout, lane, x);
-        fence_proxy_async_smem();
-        __syncwarp();                                // also orders this warp's tau stores before lane 0's release
-        if (lane == 0) { tma_store_2d(mapA, row * TB, k * TB, pout); bulk_commit(); }
-        pending = row;
-    };
 
     // ---- GEQRT on the diagonal tile
-    wait_flag(prog_col + k, k, wd);
+    wait_ready(k);
     issue(k, 0);
     mbar_wait_wd(&pfull[0], phbits & 1, wd); phbits ^= 1;
     float a[TB];
@@ -220,19 +242,36 @@ __device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int p
     tauc[k * TB + lane] = t;
 #pragma unroll
     for (int r = 0; r < TB; ++r) Rs[r * 33 + lane] = a[r];   // upper = R (updated by the chain), lower = V
-    store_tile(k, a);
+    {
+        float *pout = pout0 + (k & 1) * TB * TB;
+        store_col_sw(pout, lane, a);
+        ptau[lane] = t;
+        fence_proxy_async_smem();
+        __syncwarp();                                // also orders this warp's tau stores before lane 0's release
+        if (lane == 0) { tma_store_2d(mapA, k * TB, k * TB, pout); bulk_commit(); }
+        pending = k;
+        if (la) {                                    // UNMQR on tile (k, k+1): it stays in shared memory (ptop)
+            float x[TB];
+            load_col_sw(x, pla0, lane);
+            if (lane == 0) trace_mark(P, k, k, k + 1, 0);
+            apply_reflectors_nc<1, false, true>(x, x, nullptr, nullptr, 0, pout, ptau);
+#pragma unroll
+            for (int r = 0; r < TB; ++r) ptop[r * TB + lane] = x[r];
+            if (lane == 0) trace_mark(P, k, k, k + 1, 1);
+        }
+    }
 
     // ---- TSQRT chain down the tile column; R stays in shared memory
     bool have_cur = false;
     for (int i = k + 1; i < p; ++i) {
         const int s = (i - k) & 1;
         if (!have_cur) {
-            if (ld_relaxed(prog_col + i) < k) publish();     // about to block: do not sit on a finished tile
-            wait_flag(prog_col + i, k, wd);
+            if (!ready(i)) publish();                // about to block: do not sit on a finished tile
+            wait_ready(i);
             issue(i, s);
         }
         bool have_next = false;
-        if (i + 1 < p && ld_relaxed(prog_col + i + 1) >= k) { __threadfence(); issue(i + 1, s ^ 1); have_next = true; }
+        if (i + 1 < p && ready(i + 1)) { __threadfence(); issue(i + 1, s ^ 1); have_next = true; }
         mbar_wait_wd(&pfull[s], (phbits >> s) & 1, wd); phbits ^= 1u << s;
         float b[TB];
         load_col_sw(b, pin0 + s * TB * TB, lane);
@@ -244,21 +283,47 @@ __device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int p
         if (lane == 0) trace_mark(P, k, i, k, 1);
         publish();
         tauc[i * TB + lane] = ti;
+        float *pla = pla0 + ((i - k) % 3) * TB * TB;
+        if (la) {                                    // TSMQR on [ptop; tile (i, k+1)] with the block just built
+            ptau[lane] = ti;
+            __syncwarp();
+            float x[TB];
+            load_col_sw(x, pla, lane);
+            if (lane == 0) trace_mark(P, k, i, k + 1, 0);
+            apply_reflectors_nc<1, true, true>(x, x, ptop + lane, ptop + lane, TB, pout, ptau);
+            store_col_sw(pla, lane, x);
+        }
         fence_proxy_async_smem();
         __syncwarp();                                // also orders this warp's tau stores before lane 0's release
-        if (lane == 0) { tma_store_2d(mapA, i * TB, k * TB, pout); bulk_commit(); }
+        if (lane == 0) {
+            tma_store_2d(mapA, i * TB, k * TB, pout);
+            if (la) tma_store_2d(mapA, i * TB, (k + 1) * TB, pla);
+            bulk_commit();
+        }
         pending = i;
         have_cur = have_next;
     }
     publish();
-    // ---- final diagonal tile: R from the chain above the diagonal, GEQRT reflectors below
+    // ---- final diagonal tile: R from the chain above the diagonal, GEQRT reflectors below;
+    //      and the resident tile (k, k+1) of the look-ahead column
     float f[TB];
 #pragma unroll
     for (int r = 0; r < TB; ++r) f[r] = Rs[r * 33 + lane];
     store_col_sw(pout0, lane, f);
+    if (la) {
+#pragma unroll
+        for (int r = 0; r < TB; ++r) f[r] = ptop[r * TB + lane];
+        store_col_sw(pla0, lane, f);
+    }
     fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0) { tma_store_2d(mapA, k * TB, k * TB, pout0); bulk_commit(); bulk_wait_all(); }
+    if (lane == 0) {
+        tma_store_2d(mapA, k * TB, k * TB, pout0);
+        if (la) tma_store_2d(mapA, k * TB, (k + 1) * TB, pla0);
+        bulk_commit();
+        bulk_wait_all();
+        if (la) { __threadfence(); st_release(prog_la + k, k + 1); }
+    }
     __syncwarp();
 }
 
@@ -289,7 +354,8 @@ __device__ void sweep_loader(const Params &P, const CUtensorMap *mapA, const CUt
     const int lane = threadIdx.x & 31;
     const int p = P.p, nrows = p - k;
     const int jt = g * C::G + lane;                              // lanes 0..G-1: one tile column each
-    const bool active = lane < C::G && jt > k && jt < P.q;
+    const int kla = k + (lookahead(P, k, C::G) ? 1 : 0);         // the panel warp keeps column k+1 itself
+    const bool active = lane < C::G && jt > kla && jt < P.q;
     const unsigned amask = __ballot_sync(FULL, active);
     const uint32_t bytes = __popc(amask) * TILE_BYTES + TILE_BYTES + 128;
     const int owner = (k / C::G) % P.world;                      // rank holding the panel column of step k
@@ -334,7 +400,8 @@ __device__ void sweep_storer(const Params &P, const CUtensorMap *mapA, int k, in
     const int lane = threadIdx.x & 31;
     const int p = P.p, nrows = p - k;
     const int jt = g * C::G + lane;
-    const bool active = lane < C::G && jt > k && jt < P.q;
+    const int kla = k + (lookahead(P, k, C::G) ? 1 : 0);
+    const bool active = lane < C::G && jt > kla && jt < P.q;
 
     for (int idx = 0; idx <= nrows; ++idx) {
         const int s = ring.stage;
@@ -369,7 +436,7 @@ __device__ void sweep_consumer(const Params &P, int k, int g, const SweepCtx<NC>
 #pragma unroll
     for (int n = 0; n < NC; ++n) {
         jts[n] = g * C::G + n * CW + w;
-        act[n] = jts[n] > k && jts[n] < P.q;
+        act[n] = jts[n] > k + (lookahead(P, k, C::G) ? 1 : 0) && jts[n] < P.q;
     }
 
     for (int idx = 0; idx <= nrows; ++idx) {
@@ -482,6 +549,11 @@ tiledqr_persistent(const __grid_constant__ KernelArgs KA)
         named_bar_sync(1, SWEEP_THREADS);
         const int k = s_task[0], g = s_task[1];
         if (k < 0) break;
+        {   // a diagonal-group sweep whose only column went to the look-ahead has nothing to do
+            const int j_lo = max(g * C::G, k + 1 + (lookahead(P, k, C::G) ? 1 : 0));
+            const int j_hi = min((g + 1) * C::G, P.q);
+            if (j_lo >= j_hi) continue;
+        }
         if (warp == W_LOADER) sweep_loader<NC>(P, &mapA, mapVs, k, g, cx, ring, wd);
         else if (warp == W_STORER) sweep_storer<NC>(P, &mapA, k, g, cx, ring, wd);
         else sweep_consumer<NC>(P, k, g, cx, ring, wd);
@@ -644,6 +716,7 @@ struct b200qr_plan_s {
     int npanel_ctas;        // role split (0 = every CTA runs both roles)
     int nsweeps, npanels;   // tickets of this rank
     int rank = 0, world = 1;
+    int la_enable = 0;
     float *peer_A[MAXW];
     int *peer_prog[MAXW];
     float *peer_tauc[MAXW];
@@ -774,13 +847,13 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
         for (; want < grid / 4; ++want) {
             const double t_panel = ptiles * 8.7 / (NPW * want);
             const double t_sweep = stiles * 0.54 / ((double)world * (grid - want));
-            if (t_panel <= 0.6 * t_sweep) break;
+            if (t_panel <= 0.4 * t_sweep) break;
         }
         pl->npanel_ctas = want;
     }
     if (world == 1) {
         if (const char *e = getenv("QRB200_NP")) {
-            int v = atoi(e);
+            int v = *e ? atoi(e) : -1;
             if (v > 0 && v < grid && grid >= 2) { pl->npanel_ctas = v; } else if (v == 0) { pl->npanel_ctas = 0; pl->nc = 1; }
         }
         if (const char *e = getenv("QRB200_NC")) { int v = atoi(e); if (v == 1 || (v == 2 && pl->npanel_ctas > 0)) pl->nc = v; }
@@ -789,6 +862,8 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
     }
     const int G = CW * pl->nc;
     pl->G = G;
+    pl->la_enable = 0;
+    if (const char *e = getenv("QRB200_LOOKAHEAD")) pl->la_enable = atoi(e) != 0;
 
     // this rank's tickets: sweeps of its blocks in the global skewed order, panels of its tile columns
     long npan = 0;
@@ -842,7 +917,7 @@ static int fill_rank_ctx(RankCtx *rc, b200qr_plan_s *pl, float *dA, int ldm)
     P.tauc = pl->d_tauc; P.prog = pl->d_prog; P.ctr = pl->d_ctr;
     P.sweep_tab = pl->d_sweep_tab; P.nsweeps = pl->nsweeps; P.npanel_ctas = pl->npanel_ctas;
     P.panel_tab = pl->d_panel_tab; P.npanels = pl->npanels;
-    P.rank = pl->rank; P.world = pl->world;
+    P.rank = pl->rank; P.world = pl->world; P.la_enable = pl->la_enable;
     P.trace = pl->trace ? pl->d_trace : nullptr; P.trace_off = pl->d_trace_off; P.trace_mode = pl->trace;
     P.watchdog_ns = pl->watchdog_ns;
     for (int r = 0; r < pl->world; ++r) { P.peer_prog[r] = pl->peer_prog[r]; P.peer_tauc[r] = pl->peer_tauc[r]; }
