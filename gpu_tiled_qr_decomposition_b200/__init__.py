@@ -18,7 +18,7 @@ TASK_AVAIL, TASK_NONE, TASK_DONE = 0, 1, 2
 # every symbol include/qrb200.h and include/gpucalc_compat.h declare
 EXPORTS = (
     "b200qr_version", "b200qr_strerror", "b200qr_last_cuda_error", "b200qr_device_sm_count", "b200qr_copy",
-    "b200qr_measure_fp32_peak", "b200qr_probe_panel",
+    "b200qr_measure_fp32_peak", "b200qr_probe_panel", "b200qr_probe_umma",
     "b200qr_plan_create", "b200qr_plan_destroy", "b200qr_plan_grid", "b200qr_plan_tile_tasks",
     "b200qr_plan_macro_tasks", "b200qr_factor_device", "b200qr_plan_tau_device",
     "b200qr_tau_to_reference", "b200qr_factor_host", "b200qr_plan_read_trace", "b200qr_tile_task",
@@ -77,6 +77,7 @@ def lib():
         L.b200qr_copy.argtypes = [vp, vp, C.c_size_t]
         L.b200qr_measure_fp32_peak.argtypes = [C.POINTER(C.c_double), C.c_int]
         L.b200qr_probe_panel.argtypes = [C.POINTER(C.c_longlong), C.c_int]
+        L.b200qr_probe_umma.argtypes = [vp, vp, vp, vp, vp]
         L.b200qr_plan_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(Opts)]
         L.b200qr_plan_destroy.argtypes = [vp]
         L.b200qr_plan_grid.argtypes = [vp]

@@ -76,6 +76,10 @@ int         b200qr_measure_fp32_peak(double *gflops, int iters);
 /* SM cycles per tile of the panel kernels run by one warp: cycles4 = {GEQRT alone, TSQRT alone,
  * GEQRT / TSQRT with eight FFMA-bound warps on the same SM}.  Diagnostic for the scheduler design. */
 int         b200qr_probe_panel(long long *cycles4, int reps);
+/* tcgen05 building-block check (see csrc/umma_probe.cu): hA 32 x 128 column-major, hV 32 x 32 column-major,
+ * hW 128 x 32 row-major or NULL; hZ <- A^T V (128 x 32 row-major, 3xTF32 on the tensor cores);
+ * hD2 <- A^T - W V^T when hW is given. */
+int         b200qr_probe_umma(const float *hA, const float *hV, const float *hW, float *hZ, float *hD2);
 
 /* ---- plan: workspace + schedule for one (m, n) shape ----------------------------
  * Replaces the per-call cudaMalloc of task grid / queue / tau in cudaQRTask
