@@ -560,6 +560,10 @@ tiledqr_persistent(const __grid_constant__ KernelArgs KA)
     }
 }
 
+}  // namespace qrb200
+#include "qr_persistent_tc.cuh"
+namespace qrb200 {
+
 // ------------------------------------------------------------------ single tile tasks
 // doATask (qrdecomp.c:377-449) on device memory, one warp; used by the per-kernel parity
 // tests, doCUDADAPP and cudaQRFull.  taumat is in the reference's tau-matrix layout.
@@ -764,8 +768,15 @@ static int make_tile_map(CUtensorMap *map, float *dA, int m, int n, int ldm, boo
     return r == CUDA_SUCCESS ? B200QR_OK : B200QR_ECUDA;
 }
 
-static const void *kernel_of(int nc) { return nc == 2 ? (const void *)tiledqr_persistent<2> : (const void *)tiledqr_persistent<1>; }
-static int smem_of(int nc) { return nc == 2 ? Cfg<2>::SMEM_BYTES : Cfg<1>::SMEM_BYTES; }
+// kernel variants: 1 / 2 = SIMT sweeps with 1 / 2 matrix columns per consumer thread, 3 = tensor-core sweeps
+static const void *kernel_of(int nc)
+{
+    return nc == 3 ? (const void *)tiledqr_persistent_tc
+                   : (nc == 2 ? (const void *)tiledqr_persistent<2> : (const void *)tiledqr_persistent<1>);
+}
+static int smem_of(int nc) { return nc == 3 ? Cfg<3>::SMEM_BYTES : (nc == 2 ? Cfg<2>::SMEM_BYTES : Cfg<1>::SMEM_BYTES); }
+static int threads_of(int nc) { return nc == 3 ? tc::NTHREADS_TC : NTHREADS; }
+static int group_of(int nc) { return nc == 3 ? Cfg<3>::G : CW * nc; }
 
 extern "C" {
 
@@ -819,10 +830,10 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
     int dev = 0, sms = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    for (int nc = 1; nc <= 2; ++nc)
+    for (int nc = 1; nc <= 3; ++nc)
         CK(cudaFuncSetAttribute(kernel_of(nc), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(nc)));
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel_of(2), NTHREADS, smem_of(2)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel_of(3), threads_of(3), smem_of(3)));
     if (occ < 1) return B200QR_EINVAL;
     int grid = occ * sms / nvirt;                  // every CTA must be co-resident (cooperative launch)
     if (opts && opts->grid_ctas > 0 && opts->grid_ctas < grid) grid = opts->grid_ctas;
@@ -860,7 +871,9 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
     } else if (pl->nc == 2 && grid < 16) {
         return B200QR_EINVAL;                      // cannot honour the world-wide variant on this grid
     }
-    const int G = CW * pl->nc;
+    // tensor-core sweeps (opt-in while they are being validated): same role split, 8 tile columns per sweep
+    if (pl->nc == 2 && getenv("QRB200_TC") && atoi(getenv("QRB200_TC")) != 0) pl->nc = 3;
+    const int G = group_of(pl->nc);
     pl->G = G;
     pl->la_enable = 0;
     if (const char *e = getenv("QRB200_LOOKAHEAD")) pl->la_enable = atoi(e) != 0;
@@ -926,7 +939,7 @@ static int fill_rank_ctx(RankCtx *rc, b200qr_plan_s *pl, float *dA, int ldm)
         float *src = r == pl->rank ? dA : pl->peer_A[r];
         int ld = r == pl->rank ? ldm : pl->m;
         if (!src) return B200QR_EINVAL;            // peers not connected
-        rc_ = make_tile_map(&rc->mapV[r], src, pl->m, pl->n, ld, false);
+        rc_ = make_tile_map(&rc->mapV[r], src, pl->m, pl->n, ld, pl->nc == 3);   // tensor-core operands are swizzled
     }
     return rc_;
 }
@@ -942,7 +955,7 @@ static int reset_progress(b200qr_plan_s *pl, cudaStream_t stream)
 static int launch(KernelArgs *ka, int nc, int grid, cudaStream_t stream)
 {
     void *args[] = {ka};
-    CK(cudaLaunchCooperativeKernel(kernel_of(nc), dim3(grid), dim3(NTHREADS), args, smem_of(nc), stream));
+    CK(cudaLaunchCooperativeKernel(kernel_of(nc), dim3(grid), dim3(threads_of(nc)), args, smem_of(nc), stream));
     return B200QR_OK;
 }
 
