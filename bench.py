@@ -237,7 +237,7 @@ def run_b200_single(args):
                                    % (n, n), "parallelism": "1 GPU",
                        "l2": "input restored from a pristine %d MiB copy before every timed step (> 126 MB L2)"
                              % (4 * n * n >> 20),
-                       "persistent_grid_ctas": plan.grid, "tile_tasks": plan.tile_tasks,
+                       "persistent_grid_ctas": plan.grid, "kernel_variant": plan.variant, "tile_tasks": plan.tile_tasks,
                        "macro_tasks": plan.macro_tasks},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "GFLOP/s", "h2d_bytes_per_step": 4 * n * n,

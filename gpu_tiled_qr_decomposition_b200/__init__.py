@@ -19,7 +19,7 @@ TASK_AVAIL, TASK_NONE, TASK_DONE = 0, 1, 2
 EXPORTS = (
     "b200qr_version", "b200qr_strerror", "b200qr_last_cuda_error", "b200qr_device_sm_count", "b200qr_copy",
     "b200qr_measure_fp32_peak", "b200qr_probe_panel", "b200qr_probe_umma",
-    "b200qr_plan_create", "b200qr_plan_destroy", "b200qr_plan_grid", "b200qr_plan_tile_tasks",
+    "b200qr_plan_create", "b200qr_plan_destroy", "b200qr_plan_grid", "b200qr_plan_variant", "b200qr_plan_tile_tasks",
     "b200qr_plan_macro_tasks", "b200qr_factor_device", "b200qr_plan_tau_device",
     "b200qr_tau_to_reference", "b200qr_factor_host", "b200qr_plan_read_trace", "b200qr_tile_task",
     "b200qr_sched_init", "b200qr_sched_next", "b200qr_sched_done", "b200qr_sched_free",
@@ -81,6 +81,7 @@ def lib():
         L.b200qr_plan_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(Opts)]
         L.b200qr_plan_destroy.argtypes = [vp]
         L.b200qr_plan_grid.argtypes = [vp]
+        L.b200qr_plan_variant.argtypes = [vp]
         L.b200qr_plan_tile_tasks.argtypes = [vp]
         L.b200qr_plan_tile_tasks.restype = C.c_long
         L.b200qr_plan_macro_tasks.argtypes = [vp]
@@ -166,6 +167,10 @@ class Plan:
     @property
     def grid(self):
         return lib().b200qr_plan_grid(self._h)
+
+    @property
+    def variant(self):
+        return lib().b200qr_plan_variant(self._h)
 
     @property
     def tile_tasks(self):

@@ -562,6 +562,7 @@ tiledqr_persistent(const __grid_constant__ KernelArgs KA)
 
 }  // namespace qrb200
 #include "qr_persistent_tc.cuh"
+#include "qr_persistent_tc2.cuh"
 namespace qrb200 {
 
 // ------------------------------------------------------------------ single tile tasks
@@ -771,12 +772,17 @@ static int make_tile_map(CUtensorMap *map, float *dA, int m, int n, int ldm, boo
 // kernel variants: 1 / 2 = SIMT sweeps with 1 / 2 matrix columns per consumer thread, 3 = tensor-core sweeps
 static const void *kernel_of(int nc)
 {
-    return nc == 3 ? (const void *)tiledqr_persistent_tc
-                   : (nc == 2 ? (const void *)tiledqr_persistent<2> : (const void *)tiledqr_persistent<1>);
+    return nc == 4 ? (const void *)tiledqr_persistent_tc2
+                   : (nc == 3 ? (const void *)tiledqr_persistent_tc
+                              : (nc == 2 ? (const void *)tiledqr_persistent<2> : (const void *)tiledqr_persistent<1>));
 }
-static int smem_of(int nc) { return nc == 3 ? Cfg<3>::SMEM_BYTES : (nc == 2 ? Cfg<2>::SMEM_BYTES : Cfg<1>::SMEM_BYTES); }
-static int threads_of(int nc) { return nc == 3 ? tc::NTHREADS_TC : NTHREADS; }
-static int group_of(int nc) { return nc == 3 ? Cfg<3>::G : CW * nc; }
+static int smem_of(int nc)
+{
+    return nc == 4 ? Cfg<4>::SMEM_BYTES : (nc == 3 ? Cfg<3>::SMEM_BYTES : (nc == 2 ? Cfg<2>::SMEM_BYTES : Cfg<1>::SMEM_BYTES));
+}
+static int threads_of(int nc) { return nc == 4 ? tc2::NTHREADS_TC2 : (nc == 3 ? tc::NTHREADS_TC : NTHREADS); }
+static int group_of(int nc) { return nc == 4 ? Cfg<4>::G : (nc == 3 ? Cfg<3>::G : CW * nc); }
+constexpr int CTR_INTS = 64 + 512;     // tickets / trace / SM claim words of the 2-CTA-per-SM engine
 
 extern "C" {
 
@@ -830,8 +836,10 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
     int dev = 0, sms = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    for (int nc = 1; nc <= 3; ++nc)
+    for (int nc = 1; nc <= 4; ++nc) {
         CK(cudaFuncSetAttribute(kernel_of(nc), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(nc)));
+        CK(cudaFuncSetAttribute(kernel_of(nc), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    }
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel_of(3), threads_of(3), smem_of(3)));
     if (occ < 1) return B200QR_EINVAL;
@@ -872,7 +880,14 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
         return B200QR_EINVAL;                      // cannot honour the world-wide variant on this grid
     }
     // tensor-core sweeps (opt-in while they are being validated): same role split, 8 tile columns per sweep
-    if (pl->nc == 2 && getenv("QRB200_TC") && atoi(getenv("QRB200_TC")) != 0) pl->nc = 3;
+    if (pl->nc == 2 && getenv("QRB200_TC") && atoi(getenv("QRB200_TC")) != 0)
+        pl->nc = atoi(getenv("QRB200_TC")) == 2 && world == 1 && nvirt == 1 ? 4 : 3;
+    if (pl->nc == 4) {
+        // one CTA per SM holding two sweep engines; a panel CTA runs four panel warps
+        int want = (pl->npanel_ctas * NPW + tc2::NPW4 - 1) / tc2::NPW4;
+        if (const char *e = getenv("QRB200_NP")) { int v = *e ? atoi(e) : -1; if (v > 0 && v < grid) want = v; }
+        pl->npanel_ctas = want < 1 ? 1 : want;
+    }
     const int G = group_of(pl->nc);
     pl->G = G;
     pl->la_enable = 0;
@@ -888,8 +903,8 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
     pl->nsweeps = (int)ns;
     pl->npanels = (int)npan;
     const int useful = (pl->nsweeps > pl->npanels ? pl->nsweeps : pl->npanels) + pl->npanel_ctas;
-    if (grid > useful) grid = useful > 0 ? useful : 1;
-    if (pl->npanel_ctas >= grid) pl->npanel_ctas = grid > 1 ? grid / 2 : 0;
+    if (pl->nc != 4 && grid > useful) grid = useful > 0 ? useful : 1;
+    if (pl->nc != 4 && pl->npanel_ctas >= grid) pl->npanel_ctas = grid > 1 ? grid / 2 : 0;
     if (pl->npanel_ctas == 0) {
         if (pl->nc == 2 && world > 1) return B200QR_EINVAL;
         pl->nc = 1;
@@ -897,7 +912,7 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
     pl->grid = grid;
 
     CK(cudaMalloc(&pl->d_prog, sizeof(int) * (size_t)p * q));
-    CK(cudaMalloc(&pl->d_ctr, sizeof(int) * 64));
+    CK(cudaMalloc(&pl->d_ctr, sizeof(int) * CTR_INTS));
     CK(cudaMalloc(&pl->d_sweep_tab, sizeof(int2) * (size_t)(ns > 0 ? ns : 1)));
     if (ns > 0) CK(cudaMemcpy(pl->d_sweep_tab, tab.data(), sizeof(int2) * (size_t)ns, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&pl->d_panel_tab, sizeof(int) * (ptab.size() ? ptab.size() : 1)));
@@ -932,6 +947,7 @@ static int fill_rank_ctx(RankCtx *rc, b200qr_plan_s *pl, float *dA, int ldm)
     P.panel_tab = pl->d_panel_tab; P.npanels = pl->npanels;
     P.rank = pl->rank; P.world = pl->world; P.la_enable = pl->la_enable;
     P.trace = pl->trace ? pl->d_trace : nullptr; P.trace_off = pl->d_trace_off; P.trace_mode = pl->trace;
+    if (getenv("QRB200_ONE_ENGINE")) P.trace_mode = 7;
     P.watchdog_ns = pl->watchdog_ns;
     for (int r = 0; r < pl->world; ++r) { P.peer_prog[r] = pl->peer_prog[r]; P.peer_tauc[r] = pl->peer_tauc[r]; }
     int rc_ = make_tile_map(&rc->mapA, dA, pl->m, pl->n, ldm, true);
@@ -939,7 +955,7 @@ static int fill_rank_ctx(RankCtx *rc, b200qr_plan_s *pl, float *dA, int ldm)
         float *src = r == pl->rank ? dA : pl->peer_A[r];
         int ld = r == pl->rank ? ldm : pl->m;
         if (!src) return B200QR_EINVAL;            // peers not connected
-        rc_ = make_tile_map(&rc->mapV[r], src, pl->m, pl->n, ld, pl->nc == 3);   // tensor-core operands are swizzled
+        rc_ = make_tile_map(&rc->mapV[r], src, pl->m, pl->n, ld, pl->nc >= 3);   // tensor-core operands are swizzled
     }
     return rc_;
 }
@@ -947,7 +963,7 @@ static int fill_rank_ctx(RankCtx *rc, b200qr_plan_s *pl, float *dA, int ldm)
 static int reset_progress(b200qr_plan_s *pl, cudaStream_t stream)
 {
     CK(cudaMemsetAsync(pl->d_prog, 0, sizeof(int) * (size_t)pl->p * pl->q, stream));
-    CK(cudaMemsetAsync(pl->d_ctr, 0, sizeof(int) * 64, stream));
+    CK(cudaMemsetAsync(pl->d_ctr, 0, sizeof(int) * CTR_INTS, stream));
     if (pl->trace) CK(cudaMemsetAsync(pl->d_trace, 0xff, sizeof(int) * 2 * (size_t)pl->tile_tasks, stream));
     return B200QR_OK;
 }
@@ -978,6 +994,7 @@ int b200qr_plan_destroy(b200qr_plan_t pl)
 }
 
 int b200qr_plan_grid(b200qr_plan_t pl) { return pl ? pl->grid : B200QR_EINVAL; }
+int b200qr_plan_variant(b200qr_plan_t pl) { return pl ? pl->nc : B200QR_EINVAL; }
 long b200qr_plan_tile_tasks(b200qr_plan_t pl) { return pl ? pl->tile_tasks : B200QR_EINVAL; }
 long b200qr_plan_macro_tasks(b200qr_plan_t pl) { return pl ? (long)pl->nsweeps + pl->npanels : B200QR_EINVAL; }
 const float *b200qr_plan_tau_device(b200qr_plan_t pl) { return pl ? pl->d_tauc : nullptr; }

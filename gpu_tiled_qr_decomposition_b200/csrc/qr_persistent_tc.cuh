@@ -65,25 +65,6 @@ __device__ __forceinline__ float *sw_hi() { return reinterpret_cast<float *>(g_s
 __device__ __forceinline__ float *sw_lo() { return reinterpret_cast<float *>(g_smem + C::OFF_SW + C::G * TILE_BYTES); }
 __device__ __forceinline__ float *g_scratch() { return reinterpret_cast<float *>(g_smem + C::OFF_GS); }
 
-__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const float (&v)[32])
-{
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
-        "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
-        "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
-        "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
-        "r"(__float_as_uint(v[15])), "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])),
-        "r"(__float_as_uint(v[19])), "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])),
-        "r"(__float_as_uint(v[23])), "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])),
-        "r"(__float_as_uint(v[27])), "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])),
-        "r"(__float_as_uint(v[31]))
-        : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-
 // write a 32-float line (one matrix column's coefficients) as hi / lo operands, swizzled
 __device__ __forceinline__ void store_line_split(float *tile_hi, float *tile_lo, int line, const float (&x)[TB])
 {
@@ -435,7 +416,7 @@ __global__ void __launch_bounds__(tc::NTHREADS_TC, 1) tiledqr_persistent_tc(cons
         tma_prefetch_desc(&mapA);
         for (int r = 0; r < P.world; ++r) tma_prefetch_desc(&mapVs[r]);
     }
-    if (warp == W_MMA && !panel_cta) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == W_MMA && !panel_cta) tmem_alloc<TMEM_COLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -479,7 +460,7 @@ __global__ void __launch_bounds__(tc::NTHREADS_TC, 1) tiledqr_persistent_tc(cons
     }
     tc_fence_before();
     named_bar_sync(1, SWEEP_THREADS_TC);
-    if (warp == W_MMA) tmem_dealloc(tmem, TMEM_COLS);
+    if (warp == W_MMA) tmem_dealloc<TMEM_COLS>(tmem);
 }
 
 }  // namespace qrb200

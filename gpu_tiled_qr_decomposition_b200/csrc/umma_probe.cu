@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(const __grid_constant__
         mbar_init(&sm.bar_mma, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) tmem_alloc(&sm.tmem_slot, 64);
+    if (warp == 0) tmem_alloc<128>(&sm.tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -74,6 +74,14 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(const __grid_constant__
         store_col_sw(sm.w_hi + warp * TB * TB, tid & 31, w);
         split_line_sw(sm.w_hi, sm.w_lo, tid);
     }
+    if (mode & 4) {
+        // A operand of product 1 in tensor memory: this thread's column, hi in TMEM columns 64..95, lo in 96..127
+        float h[TB], l[TB];
+#pragma unroll
+        for (int r = 0; r < TB; ++r) { h[r] = tf32_hi(orig[r]); l[r] = orig[r] - h[r]; }
+        tmem_st_32x32(tmem + ((uint32_t)(warp * 32) << 16) + 64, h);
+        tmem_st_32x32(tmem + ((uint32_t)(warp * 32) << 16) + 96, l);
+    }
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -86,9 +94,11 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(const __grid_constant__
         const float *As[3] = {sm.a_hi, sm.a_hi, sm.a_lo};
         const float *Bs[3] = {sm.v_hi, sm.v_lo, sm.v_hi};
         bool acc = false;
+        const uint32_t At[3] = {tmem + 64, tmem + 64, tmem + 96};
         for (int pass = 0; pass < 3; ++pass)
             for (int kk = 0; kk < 4; ++kk) {
-                umma_tf32(tmem, umma_desc_sw128(As[pass], kk * 32), umma_desc_sw128(Bs[pass], kk * 32), idesc, acc);
+                if (mode & 4) umma_tf32_ts(tmem, At[pass] + kk * 8, umma_desc_sw128(Bs[pass], kk * 32), idesc, acc);
+                else umma_tf32(tmem, umma_desc_sw128(As[pass], kk * 32), umma_desc_sw128(Bs[pass], kk * 32), idesc, acc);
                 acc = true;
             }
         if (mode & 1) {
@@ -121,7 +131,7 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 64);
+    if (warp == 0) tmem_dealloc<128>(tmem);
 }
 
 }  // namespace qrb200

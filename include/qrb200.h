@@ -88,6 +88,7 @@ int         b200qr_probe_umma(const float *hA, const float *hV, const float *hW,
 int  b200qr_plan_create(b200qr_plan_t *plan, int m, int n, const b200qr_opts *opts);
 int  b200qr_plan_destroy(b200qr_plan_t plan);
 int  b200qr_plan_grid(b200qr_plan_t plan);               /* CTAs the kernel launches with */
+int  b200qr_plan_variant(b200qr_plan_t plan);            /* 1, 2: SIMT sweeps (1 / 2 columns per thread); 3, 4: tcgen05 sweeps */
 long b200qr_plan_tile_tasks(b200qr_plan_t plan);         /* sum_k (p-k)(q-k)  (gpucalc.cu:1546-1559) */
 long b200qr_plan_macro_tasks(b200qr_plan_t plan);        /* panel + column-sweep tasks actually queued */
 

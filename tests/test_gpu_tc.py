@@ -11,10 +11,10 @@ pytestmark = pytest.mark.gpu
 EPS = float(np.finfo(np.float32).eps)
 
 
-@pytest.fixture
-def tc_env():
+@pytest.fixture(params=["1", "2"])
+def tc_env(request):
     old = os.environ.get("QRB200_TC")
-    os.environ["QRB200_TC"] = "1"
+    os.environ["QRB200_TC"] = request.param
     yield
     if old is None:
         os.environ.pop("QRB200_TC", None)
@@ -29,6 +29,7 @@ def test_tc_sweeps_match_oracle(cuda, qr, po, tc_env, m, n):
     d = torch.from_numpy(a).cuda()
     dt = torch.zeros_like(d)
     plan = qr.Plan(m, n)
+    assert plan.variant == {"1": 3, "2": 4}[os.environ["QRB200_TC"]]
     s = torch.cuda.current_stream().cuda_stream
     plan.factor(d.data_ptr(), m, s)
     plan.tau_to_reference(dt.data_ptr(), m, s)
