@@ -19,12 +19,13 @@ TASK_AVAIL, TASK_NONE, TASK_DONE = 0, 1, 2
 EXPORTS = (
     "b200qr_version", "b200qr_strerror", "b200qr_last_cuda_error", "b200qr_device_sm_count", "b200qr_copy",
     "b200qr_measure_fp32_peak", "b200qr_probe_panel", "b200qr_probe_umma",
-    "b200qr_plan_create", "b200qr_plan_destroy", "b200qr_plan_grid", "b200qr_plan_variant", "b200qr_plan_tile_tasks",
+    "b200qr_plan_create", "b200qr_plan_destroy", "b200qr_plan_grid", "b200qr_plan_variant", "b200qr_plan_debug_counters", "b200qr_plan_tile_tasks",
     "b200qr_plan_macro_tasks", "b200qr_factor_device", "b200qr_plan_tau_device",
     "b200qr_tau_to_reference", "b200qr_factor_host", "b200qr_plan_read_trace", "b200qr_tile_task",
     "b200qr_sched_init", "b200qr_sched_next", "b200qr_sched_done", "b200qr_sched_free",
     "b200qr_sched_progress", "b200qr_sched_ready_count", "b200qr_sched_dep_count",
-    "b200qr_sched_predecessors", "b200qr_sched_device_order", "b200qr_sched_sweep_order", "b200qr_sched_rank_tickets",
+    "b200qr_sched_predecessors", "b200qr_sched_device_order", "b200qr_sched_sweep_order", "b200qr_sched_rank_tickets", "b200qr_sched_sweep_order_skew",
+    "b200qr_sched_rank_tickets_skew",
     "b200qr_dist_create", "b200qr_dist_destroy", "b200qr_dist_handle_bytes", "b200qr_dist_export",
     "b200qr_dist_connect", "b200qr_dist_matrix", "b200qr_dist_tau_device", "b200qr_dist_block",
     "b200qr_dist_owner", "b200qr_dist_grid", "b200qr_dist_read_trace", "b200qr_dist_tile_tasks", "b200qr_dist_reset", "b200qr_dist_factor",
@@ -82,6 +83,7 @@ def lib():
         L.b200qr_plan_destroy.argtypes = [vp]
         L.b200qr_plan_grid.argtypes = [vp]
         L.b200qr_plan_variant.argtypes = [vp]
+        L.b200qr_plan_debug_counters.argtypes = [vp, vp, C.c_int]
         L.b200qr_plan_tile_tasks.argtypes = [vp]
         L.b200qr_plan_tile_tasks.restype = C.c_long
         L.b200qr_plan_macro_tasks.argtypes = [vp]

@@ -894,11 +894,15 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
     if (const char *e = getenv("QRB200_LOOKAHEAD")) pl->la_enable = atoi(e) != 0;
 
     // this rank's tickets: sweeps of its blocks in the global skewed order, panels of its tile columns
+    // skew of the sweep order: a tensor-core sweep row is several times faster than a TSQRT of the panel
+    // chain, so its panel needs a longer head start than one distribution block of steps
+    int skew = pl->nc == 4 ? 32 : G;
+    if (const char *e = getenv("QRB200_SKEW")) { int v = atoi(e); if (v > 0) skew = v; }
     long npan = 0;
-    const long ns = b200qr_sched_rank_tickets(p, q, G, rank, world, nullptr, 0, nullptr, 0, &npan);
+    const long ns = b200qr_sched_rank_tickets_skew(p, q, G, skew, rank, world, nullptr, 0, nullptr, 0, &npan);
     if (ns < 0) return B200QR_EINVAL;
     std::vector<int> tab(2 * (size_t)(ns > 0 ? ns : 1)), ptab((size_t)(npan > 0 ? npan : 1));
-    b200qr_sched_rank_tickets(p, q, G, rank, world, tab.data(), ns, ptab.data(), npan, &npan);
+    b200qr_sched_rank_tickets_skew(p, q, G, skew, rank, world, tab.data(), ns, ptab.data(), npan, &npan);
     ptab.resize((size_t)npan);
     pl->nsweeps = (int)ns;
     pl->npanels = (int)npan;
@@ -920,7 +924,7 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
     CK(cudaMalloc(&pl->d_tauc, sizeof(float) * (size_t)K * p * TB));
     CK(cudaMemset(pl->d_tauc, 0, sizeof(float) * (size_t)K * p * TB));
     CK(cudaMemset(pl->d_prog, 0, sizeof(int) * (size_t)p * q));
-    if (pl->trace) {
+    if (pl->trace && pl->trace != 3) {
         CK(cudaMalloc(&pl->d_trace, sizeof(int) * 2 * (size_t)tiles));
         CK(cudaMalloc(&pl->d_trace_off, sizeof(long long) * K));
         CK(cudaMemcpy(pl->d_trace_off, pl->trace_off.data(), sizeof(long long) * K, cudaMemcpyHostToDevice));
@@ -946,7 +950,7 @@ static int fill_rank_ctx(RankCtx *rc, b200qr_plan_s *pl, float *dA, int ldm)
     P.sweep_tab = pl->d_sweep_tab; P.nsweeps = pl->nsweeps; P.npanel_ctas = pl->npanel_ctas;
     P.panel_tab = pl->d_panel_tab; P.npanels = pl->npanels;
     P.rank = pl->rank; P.world = pl->world; P.la_enable = pl->la_enable;
-    P.trace = pl->trace ? pl->d_trace : nullptr; P.trace_off = pl->d_trace_off; P.trace_mode = pl->trace;
+    P.trace = (pl->trace && pl->trace != 3) ? pl->d_trace : nullptr; P.trace_off = pl->d_trace_off; P.trace_mode = pl->trace;
     if (getenv("QRB200_ONE_ENGINE")) P.trace_mode = 7;
     P.watchdog_ns = pl->watchdog_ns;
     for (int r = 0; r < pl->world; ++r) { P.peer_prog[r] = pl->peer_prog[r]; P.peer_tauc[r] = pl->peer_tauc[r]; }
@@ -964,7 +968,7 @@ static int reset_progress(b200qr_plan_s *pl, cudaStream_t stream)
 {
     CK(cudaMemsetAsync(pl->d_prog, 0, sizeof(int) * (size_t)pl->p * pl->q, stream));
     CK(cudaMemsetAsync(pl->d_ctr, 0, sizeof(int) * CTR_INTS, stream));
-    if (pl->trace) CK(cudaMemsetAsync(pl->d_trace, 0xff, sizeof(int) * 2 * (size_t)pl->tile_tasks, stream));
+    if (pl->trace && pl->trace != 3) CK(cudaMemsetAsync(pl->d_trace, 0xff, sizeof(int) * 2 * (size_t)pl->tile_tasks, stream));
     return B200QR_OK;
 }
 
@@ -995,6 +999,12 @@ int b200qr_plan_destroy(b200qr_plan_t pl)
 
 int b200qr_plan_grid(b200qr_plan_t pl) { return pl ? pl->grid : B200QR_EINVAL; }
 int b200qr_plan_variant(b200qr_plan_t pl) { return pl ? pl->nc : B200QR_EINVAL; }
+int b200qr_plan_debug_counters(b200qr_plan_t pl, unsigned long long *out, int n)
+{
+    if (!pl || !out || n < 1 || n > 8) return B200QR_EINVAL;
+    CK(cudaMemcpy(out, pl->d_ctr + 32, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost));
+    return B200QR_OK;
+}
 long b200qr_plan_tile_tasks(b200qr_plan_t pl) { return pl ? pl->tile_tasks : B200QR_EINVAL; }
 long b200qr_plan_macro_tasks(b200qr_plan_t pl) { return pl ? (long)pl->nsweeps + pl->npanels : B200QR_EINVAL; }
 const float *b200qr_plan_tau_device(b200qr_plan_t pl) { return pl ? pl->d_tauc : nullptr; }

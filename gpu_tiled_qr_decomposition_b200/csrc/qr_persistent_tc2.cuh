@@ -50,7 +50,8 @@ __device__ __forceinline__ unsigned char *eng_smem() { return g_smem + (threadId
 __device__ __forceinline__ uint32_t tm_ah(int par) { return (uint32_t)(par * 96); }
 __device__ __forceinline__ uint32_t tm_al(int par) { return (uint32_t)(par * 96 + 32); }
 __device__ __forceinline__ uint32_t tm_zp(int par) { return (uint32_t)(par * 96 + 64); }
-__device__ __forceinline__ uint32_t tm_g(int par) { return (uint32_t)(192 + par * 32); }
+__device__ __forceinline__ uint32_t tm_g(int) { return 192u; }          // one buffer: the helper reads it before it stages the next row
+__device__ __forceinline__ uint32_t tm_ctop() { return 224u; }           // the resident tile row k, one column per thread
 
 struct Bars {   // per engine
     static constexpr int FULL = 0, COMPUTED = 3, EMPTY = 6, GREADY = 9, SPLIT = 12, ZREADY = 14, WSTORED = 16, PREADY = 18,
@@ -188,6 +189,9 @@ __device__ void helper(const Params &P, int k, uint32_t tmem, Ctr &rc, const Wat
         tc_fence_after();
         float grow[TB];
         tmem_ld_32x32(grow, tmem + tm_g(par));                       // lane j: (V^T V)[j][0..31]
+        const float tj = tau_s(s)[lane];
+#pragma unroll
+        for (int c = 0; c < TB; ++c) grow[c] *= tj;                  // tau_j folded in: the chain below is FMAs only
         store_col_smem(vx(s, G_F32) + lane * TB, grow);             // row-major: consumers read row j as a broadcast
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(Bars::GREADY + s));
@@ -244,6 +248,8 @@ __device__ void mma_issuer(const Params &P, int k, uint32_t tmem, Ctr &rc, const
     for (int idx = 0; idx < nrows; ++idx) {
         const int s = rc.stage(), par = rc.par();
         const uint32_t th = umma_desc_lo(vx(s, VT_HI)), tl = umma_desc_lo(vx(s, VT_LO));
+        // the next row's first products are staged a chain step ahead (same order as the consumers' arrivals)
+        if (idx + 1 < nrows) issue_gz((rc.n + 1) % 3, par ^ 1, (uint32_t)((rc.r + 1) >> 1) & 1);
         // P = W V^T (W in the operand columns of this parity, written by the consumers)
         mbar_wait_wd(bar(Bars::WSTORED + par), rc.tm_par(), wd);
         tc_fence_after();
@@ -252,7 +258,6 @@ __device__ void mma_issuer(const Params &P, int k, uint32_t tmem, Ctr &rc, const
             umma_commit(bar(Bars::PREADY + par));
         }
         __syncwarp();
-        if (idx + 1 < nrows) issue_gz((rc.n + 1) % 3, par ^ 1, (uint32_t)((rc.r + 1) >> 1) & 1);
         rc.reflector_done();
     }
     rc.writeback_done();
@@ -266,12 +271,14 @@ __device__ void consumer(const Params &P, int k, int g, uint32_t tmem, Ctr &rc, 
     const int jt = g * C::G + w;
     const bool act = jt > k + (lookahead(P, k, C::G) ? 1 : 0) && jt < P.q;
     const uint32_t lane_base = (uint32_t)(w * 32) << 16;
-    float ctop[TB];
-#pragma unroll
-    for (int r = 0; r < TB; ++r) ctop[r] = 0.f;
+    // optional phase timers (opts.trace == 3): nanoseconds waited per barrier kind, summed over the run by
+    // lane 0 of consumer warp 0 of every engine into ctr[32..]: FULL, ZREADY, GREADY, PREADY, total, rows
+    const bool prof = P.trace_mode == 3 && w == 0 && lane == 0;
+    unsigned long long t_full = 0, t_z = 0, t_g = 0, t_p = 0, t_begin = prof ? gtimer() : 0;
+#define TIMED(acc, stmt) do { unsigned long long t0_ = prof ? gtimer() : 0; stmt; if (prof) acc += gtimer() - t0_; } while (0)
 
     auto split_row = [&](int s, uint32_t ring_par, int par) {    // operands of Z = V^T c_bot into tensor memory
-        mbar_wait_wd(bar(Bars::FULL + s), ring_par, wd);
+        TIMED(t_full, mbar_wait_wd(bar(Bars::FULL + s), ring_par, wd));
         if (act) {
             float x[TB];
             load_col_sw(x, a_tile(s, w), lane);
@@ -282,7 +289,7 @@ __device__ void consumer(const Params &P, int k, int g, uint32_t tmem, Ctr &rc, 
     };
     // finish row `prev`: c_bot -= p (or, for the UNMQR row, the result becomes the resident tile row)
     auto finish_row = [&](int s_prev, int par_prev, uint32_t tpar_prev, bool prev_is_diag) {
-        mbar_wait_wd(bar(Bars::PREADY + par_prev), tpar_prev, wd);
+        TIMED(t_p, mbar_wait_wd(bar(Bars::PREADY + par_prev), tpar_prev, wd));
         tc_fence_after();
         if (act) {
             float pr[TB], x[TB];
@@ -290,7 +297,8 @@ __device__ void consumer(const Params &P, int k, int g, uint32_t tmem, Ctr &rc, 
             load_col_sw(x, a_tile(s_prev, w), lane);
             if (prev_is_diag) {
 #pragma unroll
-                for (int r = 0; r < TB; ++r) ctop[r] = x[r] - pr[r];
+                for (int r = 0; r < TB; ++r) x[r] -= pr[r];
+                tmem_st_32x32(tmem + lane_base + tm_ctop(), x);      // the UNMQR result is the resident tile row
             } else {
 #pragma unroll
                 for (int r = 0; r < TB; ++r) x[r] -= pr[r];
@@ -309,48 +317,58 @@ __device__ void consumer(const Params &P, int k, int g, uint32_t tmem, Ctr &rc, 
     for (int idx = 0; idx < nrows; ++idx) {
         const int s = rc.stage(), par = rc.par();
         const uint32_t tpar = rc.tm_par();
-        // the resident row must be complete before the first TSMQR row adds it in
-        if (idx == 1) { finish_row(s_prev, par_prev, tpar_prev, true); have_prev = false; }
+        // previous row: subtract its product (for the UNMQR row the result becomes the resident tile row),
+        // release its stage; then stage the next row's operands -- a whole chain step ahead of their use
+        if (have_prev) finish_row(s_prev, par_prev, tpar_prev, idx == 1);
+        if (idx + 1 < nrows) split_row((rc.n + 1) % 3, (uint32_t)((rc.n + 1) / 3) & 1, par ^ 1);
         // z = V^T c_bot
-        mbar_wait_wd(bar(Bars::ZREADY + par), tpar, wd);
+        TIMED(t_z, mbar_wait_wd(bar(Bars::ZREADY + par), tpar, wd));
         tc_fence_after();
         float sv[TB];
         if (act) {
             tmem_ld_32x32(sv, tmem + lane_base + tm_zp(par));
             if (idx > 0) {
+                float ct[TB];
+                tmem_ld_32x32(ct, tmem + lane_base + tm_ctop());
 #pragma unroll
-                for (int r = 0; r < TB; ++r) sv[r] += ctop[r];
+                for (int r = 0; r < TB; ++r) sv[r] += ct[r];
             }
         }
         // w_c = tau_c (s_c - sum_{j<c} G[j][c] w_j): the reference's reflector-by-reflector recurrence
-        mbar_wait_wd(bar(Bars::GREADY + s), rc.u[s] & 1, wd);
+        TIMED(t_g, mbar_wait_wd(bar(Bars::GREADY + s), rc.u[s] & 1, wd));
         if (act) {
-            const float *gm = vx(s, G_F32), *ts = tau_s(s);
+            // sv_c -= (tau_j G[j][c]) sv_j for j < c, in order; then w_j = tau_j sv_j
+            const float *gm = vx(s, G_F32);
 #pragma unroll
-            for (int j = 0; j < TB; ++j) {
-                const float wj = ts[j] * sv[j];
-                sv[j] = wj;
+            for (int j = 0; j < TB - 1; ++j) {
+                const float sj = sv[j];
 #pragma unroll
                 for (int c4 = (j + 1) & ~3; c4 < TB; c4 += 4) {
                     const float4 g4 = *reinterpret_cast<const float4 *>(gm + j * TB + c4);
-                    if (c4 + 0 > j) sv[c4 + 0] = fmaf(-g4.x, wj, sv[c4 + 0]);
-                    if (c4 + 1 > j) sv[c4 + 1] = fmaf(-g4.y, wj, sv[c4 + 1]);
-                    if (c4 + 2 > j) sv[c4 + 2] = fmaf(-g4.z, wj, sv[c4 + 2]);
-                    if (c4 + 3 > j) sv[c4 + 3] = fmaf(-g4.w, wj, sv[c4 + 3]);
+                    if (c4 + 0 > j) sv[c4 + 0] = fmaf(-g4.x, sj, sv[c4 + 0]);
+                    if (c4 + 1 > j) sv[c4 + 1] = fmaf(-g4.y, sj, sv[c4 + 1]);
+                    if (c4 + 2 > j) sv[c4 + 2] = fmaf(-g4.z, sj, sv[c4 + 2]);
+                    if (c4 + 3 > j) sv[c4 + 3] = fmaf(-g4.w, sj, sv[c4 + 3]);
                 }
             }
-            if (idx > 0) {
+            {
+                float tv[TB];
+                load_col_smem(tv, tau_s(s));
 #pragma unroll
-                for (int r = 0; r < TB; ++r) ctop[r] -= sv[r];
+                for (int r = 0; r < TB; ++r) sv[r] *= tv[r];
+            }
+            if (idx > 0) {
+                float ct[TB];
+                tmem_ld_32x32(ct, tmem + lane_base + tm_ctop());
+#pragma unroll
+                for (int r = 0; r < TB; ++r) ct[r] -= sv[r];
+                tmem_st_32x32(tmem + lane_base + tm_ctop(), ct);
             }
             // W becomes the A operand of P = W V^T (the c_bot operands of this parity are dead: Z is complete)
             tmem_st_split(tmem + lane_base + tm_ah(par), tmem + lane_base + tm_al(par), sv);
         }
         tc_fence_before();
         mbar_arrive(bar(Bars::WSTORED + par));
-        // previous row: subtract its product, release its stage; then stage the next row's operands
-        if (have_prev) finish_row(s_prev, par_prev, tpar_prev, false);
-        if (idx + 1 < nrows) split_row((rc.n + 1) % 3, (uint32_t)((rc.n + 1) / 3) & 1, par ^ 1);
         have_prev = true; s_prev = s; par_prev = par; tpar_prev = tpar;
         rc.reflector_done();
     }
@@ -359,11 +377,21 @@ __device__ void consumer(const Params &P, int k, int g, uint32_t tmem, Ctr &rc, 
     {
         const int s = rc.stage();
         mbar_wait_wd(bar(Bars::FULL + s), rc.ring_par(), wd);
-        if (act) store_col_sw(a_tile(s, w), lane, ctop);
+        if (act) {
+            float ct[TB];
+            tmem_ld_32x32(ct, tmem + lane_base + tm_ctop());
+            store_col_sw(a_tile(s, w), lane, ct);
+        }
         fence_proxy_async_smem();
         mbar_arrive(bar(Bars::COMPUTED + s));
         rc.writeback_done();
     }
+    if (prof) {
+        unsigned long long *dbg = reinterpret_cast<unsigned long long *>(P.ctr + 32);
+        atomicAdd(dbg + 0, t_full); atomicAdd(dbg + 1, t_z); atomicAdd(dbg + 2, t_g); atomicAdd(dbg + 3, t_p);
+        atomicAdd(dbg + 4, gtimer() - t_begin); atomicAdd(dbg + 5, (unsigned long long)nrows);
+    }
+#undef TIMED
 }
 
 }  // namespace tc2

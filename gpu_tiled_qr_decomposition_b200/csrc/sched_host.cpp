@@ -135,21 +135,30 @@ int b200qr_sched_predecessors(const b200qr_task *t, b200qr_task pred[3])
 // out2 receives (k, g) pairs; returns the number of sweeps.
 long b200qr_sched_sweep_order(int M, int N, int G, int *out2, long cap)
 {
-    if (M <= 0 || N <= 0 || G <= 0) return -1;
+    return b200qr_sched_sweep_order_skew(M, N, G, G, out2, cap);
+}
+
+// Same with an explicit skew B: key(k,g) = k + B*g.  Any B >= 0 keeps the order topological (for a
+// fixed group the key grows with k, and S(k-1, diagonal group) precedes every S(k, .)); a larger B
+// hands the groups right of the diagonal out later, i.e. gives their panel a longer head start --
+// needed when a sweep row is much faster than a TSQRT of the panel chain (tensor-core sweeps).
+long b200qr_sched_sweep_order_skew(int M, int N, int G, int B, int *out2, long cap)
+{
+    if (M <= 0 || N <= 0 || G <= 0 || B < 0) return -1;
     const int K = M < N ? M : N;
     const int GB = (N + G - 1) / G;
     // counting sort on key in [0, K + G*GB]
-    std::vector<long> count((size_t)K + (size_t)G * GB + 2, 0);
+    std::vector<long> count((size_t)K + (size_t)B * GB + 2, 0);
     long n = 0;
     for (int k = 0; k < K; ++k) {
         if (k + 1 >= N) continue;
-        for (int g = (k + 1) / G; g < GB; ++g) { ++count[(size_t)k + (size_t)G * g + 1]; ++n; }
+        for (int g = (k + 1) / G; g < GB; ++g) { ++count[(size_t)k + (size_t)B * g + 1]; ++n; }
     }
     for (size_t i = 1; i < count.size(); ++i) count[i] += count[i - 1];
     for (int k = 0; k < K; ++k) {                       // k ascending => ties keep smaller k first
         if (k + 1 >= N) continue;
         for (int g = (k + 1) / G; g < GB; ++g) {
-            long pos = count[(size_t)k + (size_t)G * g]++;
+            long pos = count[(size_t)k + (size_t)B * g]++;
             if (pos < cap) { out2[2 * pos] = k; out2[2 * pos + 1] = g; }
         }
     }
@@ -164,11 +173,17 @@ long b200qr_sched_sweep_order(int M, int N, int G, int *out2, long cap)
 long b200qr_sched_rank_tickets(int M, int N, int G, int rank, int world, int *sweeps2, long cap, int *panels, long capp,
                                long *npanels)
 {
+    return b200qr_sched_rank_tickets_skew(M, N, G, G, rank, world, sweeps2, cap, panels, capp, npanels);
+}
+
+long b200qr_sched_rank_tickets_skew(int M, int N, int G, int B, int rank, int world, int *sweeps2, long cap, int *panels,
+                                    long capp, long *npanels)
+{
     if (world < 1 || rank < 0 || rank >= world) return -1;
-    long total = b200qr_sched_sweep_order(M, N, G, nullptr, 0);
+    long total = b200qr_sched_sweep_order_skew(M, N, G, B, nullptr, 0);
     if (total < 0) return -1;
     std::vector<int> all(2 * (size_t)(total > 0 ? total : 1));
-    b200qr_sched_sweep_order(M, N, G, all.data(), total);
+    b200qr_sched_sweep_order_skew(M, N, G, B, all.data(), total);
     long n = 0;
     for (long t = 0; t < total; ++t)
         if (all[2 * t + 1] % world == rank) {

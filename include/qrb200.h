@@ -88,6 +88,7 @@ int         b200qr_probe_umma(const float *hA, const float *hV, const float *hW,
 int  b200qr_plan_create(b200qr_plan_t *plan, int m, int n, const b200qr_opts *opts);
 int  b200qr_plan_destroy(b200qr_plan_t plan);
 int  b200qr_plan_grid(b200qr_plan_t plan);               /* CTAs the kernel launches with */
+int  b200qr_plan_debug_counters(b200qr_plan_t plan, unsigned long long *out, int n);   /* opts.trace == 3: phase timers of the tensor-core engine */
 int  b200qr_plan_variant(b200qr_plan_t plan);            /* 1, 2: SIMT sweeps (1 / 2 columns per thread); 3, 4: tcgen05 sweeps */
 long b200qr_plan_tile_tasks(b200qr_plan_t plan);         /* sum_k (p-k)(q-k)  (gpucalc.cu:1546-1559) */
 long b200qr_plan_macro_tasks(b200qr_plan_t plan);        /* panel + column-sweep tasks actually queued */
@@ -205,6 +206,10 @@ int  b200qr_sched_predecessors(const b200qr_task *t, b200qr_task pred[3]);
 /* Sweep ticket order of the persistent kernel for an M x N tile grid and G tile columns per
  * sweep: (k, g) pairs sorted by k + G*g.  Returns the number of sweeps (out2 may be NULL).    */
 long b200qr_sched_sweep_order(int M, int N, int G, int *out2, long cap);
+/* Same with an explicit skew B (key k + B*g; B = G above): any B >= 0 is a topological order.       */
+long b200qr_sched_sweep_order_skew(int M, int N, int G, int B, int *out2, long cap);
+long b200qr_sched_rank_tickets_skew(int M, int N, int G, int B, int rank, int world, int *sweeps2, long cap, int *panels,
+                                    long capp, long *npanels);
 /* Tickets of one rank of the block-cyclic distribution (block g of G tile columns on rank g % world):
  * its sweeps (k, g) in the global order and its panels k, ascending.  Returns the sweep count.  */
 long b200qr_sched_rank_tickets(int M, int N, int G, int rank, int world, int *sweeps2, long cap, int *panels,
