@@ -53,6 +53,10 @@ __device__ __forceinline__ void st_release(int *p, int v)
 {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed(int *p, int v)
+{
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -72,6 +76,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// non-blocking test (try_wait may suspend the thread for a while before it reports failure)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
@@ -407,6 +424,94 @@ __device__ __forceinline__ void apply_reflectors_nc(float (&b0)[TB], float (&b1)
 #pragma unroll
             for (int r = 0; r < TB; ++r) b1[r] = fmaf(-beta, v[r], b1[r]);
         }
+    }
+}
+
+// ------------------------------------------------------------------ compact-WY T factor of one block
+// The tensor-core sweep engine (qr_persistent_tc3.cuh) applies a block of 32 reflectors as
+// C -= V (T^T (V^T C)) -- the reference's reflector-by-reflector update (qrdecomp.c:620-644, 736-762)
+// in compact-WY form, which the reference itself never forms:
+//     T[c][c] = tau_c,   T[0:c, c] = -tau_c T[0:c, 0:c] (V[:, 0:c]^T v_c),
+// with V^T v_c = G[:, c], G = V^T V (for a TSQRT block V = [I; V2] the identity part contributes
+// nothing off the diagonal, so G = V2^T V2 there).  One warp, lane = reflector c:
+//   vsw   the block in the 128B-swizzled TMA tile layout (reflector j = line j); UNIT: a raw GEQRT
+//         tile (R above the diagonal) -- the implied zeros / unit diagonal are substituted;
+//   gt    32x32 floats of scratch;
+//   ops   six swizzled output tiles, the B operands of the sweeps' three products already split into
+//         their 3xTF32 halves (hi = tf32(x), lo = x - hi): V hi, V lo (line c = reflector c), T hi, T lo
+//         (column-major: line c = column c of T), V^T hi, V^T lo (line r = tile row r, entry j = V(r, j)).
+__device__ __forceinline__ float tf32_round(float a) { return __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u); }
+constexpr int OPS_V = 0, OPS_T = 2, OPS_VT = 4;      // tile index of the hi half; lo follows
+template <bool UNIT>
+__device__ __forceinline__ void build_t_warp(const float *vsw, float tau, float *gt, float *ops, int lane)
+{
+    float v[TB];
+    load_col_sw(v, vsw, lane);
+    if (UNIT) {
+#pragma unroll
+        for (int r = 0; r < TB; ++r) v[r] = (r > lane) ? v[r] : ((r == lane) ? 1.0f : 0.f);
+    }
+    {   // V (line = lane) and V^T (element lane of every line)
+        float *vh = ops + OPS_V * TB * TB, *vl = vh + TB * TB, *th = ops + OPS_VT * TB * TB, *tl = th + TB * TB;
+        char *bh = reinterpret_cast<char *>(vh) + lane * 128, *bl = reinterpret_cast<char *>(vl) + lane * 128;
+        const int sw = (lane & 7) << 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 h = make_float4(tf32_round(v[4 * i]), tf32_round(v[4 * i + 1]), tf32_round(v[4 * i + 2]), tf32_round(v[4 * i + 3]));
+            *reinterpret_cast<float4 *>(bh + ((i << 4) ^ sw)) = h;
+            *reinterpret_cast<float4 *>(bl + ((i << 4) ^ sw)) = make_float4(v[4 * i] - h.x, v[4 * i + 1] - h.y, v[4 * i + 2] - h.z, v[4 * i + 3] - h.w);
+        }
+#pragma unroll
+        for (int r = 0; r < TB; ++r) {
+            const int off = r * TB + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3));
+            const float h = tf32_round(v[r]);
+            th[off] = h;
+            tl[off] = v[r] - h;
+        }
+    }
+    // row `lane` of G^T: G[j][lane] = v_j . v_lane, element j of the row in chunk (j >> 2) ^ (lane & 7)
+    {
+        float *grow = gt + lane * TB;
+#pragma unroll 2
+        for (int j = 0; j < TB; ++j) {
+            float x[TB];
+            const char *base = reinterpret_cast<const char *>(vsw) + j * 128;
+            const int sw = (j & 7) << 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 t4 = *reinterpret_cast<const float4 *>(base + ((i << 4) ^ sw));
+                x[4 * i] = t4.x; x[4 * i + 1] = t4.y; x[4 * i + 2] = t4.z; x[4 * i + 3] = t4.w;
+            }
+            if (UNIT) {
+#pragma unroll
+                for (int r = 0; r < TB; ++r) x[r] = (r > j) ? x[r] : ((r == j) ? 1.0f : 0.f);
+            }
+            grow[(((j >> 2) ^ (lane & 7)) << 2) | (j & 3)] = dot32(v, x);
+        }
+    }
+    __syncwarp();
+    // row `lane` of T, column by column (four partial sums keep the FMA chain short)
+    float *toh = ops + OPS_T * TB * TB, *tol = toh + TB * TB;
+    float t[TB];
+#pragma unroll
+    for (int c = 0; c < TB; ++c) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const char *grow = reinterpret_cast<const char *>(gt) + c * 128;      // G[0..31][c]
+        const int sw = (c & 7) << 4;
+#pragma unroll
+        for (int j4 = 0; j4 < c; j4 += 4) {
+            const float4 g4 = *reinterpret_cast<const float4 *>(grow + ((j4 << 2) ^ sw));
+            a0 = fmaf(t[j4], g4.x, a0);
+            if (j4 + 1 < c) a1 = fmaf(t[j4 + 1], g4.y, a1);
+            if (j4 + 2 < c) a2 = fmaf(t[j4 + 2], g4.z, a2);
+            if (j4 + 3 < c) a3 = fmaf(t[j4 + 3], g4.w, a3);
+        }
+        const float tc_ = __shfl_sync(FULL, tau, c);
+        t[c] = (c == lane) ? tc_ : ((c > lane) ? -tc_ * ((a0 + a1) + (a2 + a3)) : 0.f);
+        const int off = c * TB + ((((lane >> 2) ^ (c & 7)) << 2) | (lane & 3));
+        const float h = tf32_round(t[c]);
+        toh[off] = h;
+        tol[off] = t[c] - h;
     }
 }
 

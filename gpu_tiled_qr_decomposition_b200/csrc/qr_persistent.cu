@@ -89,6 +89,7 @@ struct Cfg {
     static constexpr int OFF_PANEL = NC == 2 ? 0 : SWEEP_END;
     static constexpr int OFF_BAR = NC == 2 ? SWEEP_END : SWEEP_END + NPW * PANEL_BYTES;
     static constexpr int SMEM_BYTES = OFF_BAR + 256;
+    static constexpr bool BUILD_T = false;            // panel warps also emit the compact-WY T factors (tensor-core engine 3)
 };
 
 // The CTA's dynamic shared memory (no static __shared__ in this kernel, so it starts at offset 0
@@ -100,6 +101,8 @@ struct RankCtx {
     Params P;
     CUtensorMap mapA;               // this rank's matrix, 128B-swizzled tiles (thread-per-column access)
     CUtensorMap mapV[MAXW];         // every rank's matrix, dense tiles (reflector tiles, broadcast reads)
+    CUtensorMap mapW;               // tensor-core engine 3: workspace of pre-split operand tiles (six column blocks)
+    int wcols;                      // columns per block of that workspace (K * 32)
 };
 struct alignas(64) KernelArgs {
     int nvirt;                      // ranks emulated by this launch: CTA b works for rank slot b % nvirt
@@ -175,7 +178,8 @@ __device__ __forceinline__ bool lookahead(const Params &P, int k, int G)
 
 // ------------------------------------------------------------------ P(k): the panel warp
 template <int NC>
-__device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int pw, uint32_t &phbits, const Watch &wd)
+__device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int pw, uint32_t &phbits, const Watch &wd,
+                          const CUtensorMap *mapW = nullptr, int wcols = 0)
 {
     using C = Cfg<NC>;
     const int lane = threadIdx.x & 31;
@@ -188,6 +192,13 @@ __device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int p
     float *ptau = reinterpret_cast<float *>(mine + 4 * TILE_BYTES + 4608); // tau of the current block
     float *ptop = reinterpret_cast<float *>(mine + 4 * TILE_BYTES + 5120); // look-ahead: tile (k, k+1), [c][lane]
     float *pla0 = reinterpret_cast<float *>(mine + 5 * TILE_BYTES + 5120); // look-ahead: 3 in/out slots
+    // BUILD_T (no look-ahead there): the slots behind the broadcast area stage the six operand tiles and the Gram
+    // scratch of build_t_warp (PANEL_BYTES of that configuration has room for seven tiles there)
+    float *opstage = ptop, *gscratch = ptop + 6 * TB * TB;
+    auto store_ops = [&](int row) {                  // lane 0: the six operand tiles -> workspace column blocks
+#pragma unroll
+        for (int w = 0; w < 6; ++w) tma_store_2d(mapW, row * TB, w * wcols + k * TB, opstage + w * TB * TB);
+    };
     uint64_t *pfull = reinterpret_cast<uint64_t *>(g_smem + C::OFF_BAR) + 3 * C::NS + 2 * pw;
     int *prog_col = P.prog + (size_t)k * p;
     int *prog_la = P.prog + (size_t)(k + 1) * p;
@@ -246,9 +257,17 @@ __device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int p
         float *pout = pout0 + (k & 1) * TB * TB;
         store_col_sw(pout, lane, a);
         ptau[lane] = t;
+        if (C::BUILD_T) {
+            __syncwarp();
+            build_t_warp<true>(pout, t, gscratch, opstage, lane);
+        }
         fence_proxy_async_smem();
         __syncwarp();                                // also orders this warp's tau stores before lane 0's release
-        if (lane == 0) { tma_store_2d(mapA, k * TB, k * TB, pout); bulk_commit(); }
+        if (lane == 0) {
+            tma_store_2d(mapA, k * TB, k * TB, pout);
+            if (C::BUILD_T) store_ops(k);
+            bulk_commit();
+        }
         pending = k;
         if (la) {                                    // UNMQR on tile (k, k+1): it stays in shared memory (ptop)
             float x[TB];
@@ -283,6 +302,10 @@ __device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int p
         if (lane == 0) trace_mark(P, k, i, k, 1);
         publish();
         tauc[i * TB + lane] = ti;
+        if (C::BUILD_T) {
+            __syncwarp();                            // lane 0 has waited for the previous tile's stores: the stages are free
+            build_t_warp<false>(pout, ti, gscratch, opstage, lane);
+        }
         float *pla = pla0 + ((i - k) % 3) * TB * TB;
         if (la) {                                    // TSMQR on [ptop; tile (i, k+1)] with the block just built
             ptau[lane] = ti;
@@ -298,6 +321,7 @@ __device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int p
         if (lane == 0) {
             tma_store_2d(mapA, i * TB, k * TB, pout);
             if (la) tma_store_2d(mapA, i * TB, (k + 1) * TB, pla);
+            if (C::BUILD_T) store_ops(i);
             bulk_commit();
         }
         pending = i;
@@ -563,6 +587,7 @@ tiledqr_persistent(const __grid_constant__ KernelArgs KA)
 }  // namespace qrb200
 #include "qr_persistent_tc.cuh"
 #include "qr_persistent_tc2.cuh"
+#include "qr_persistent_tc3.cuh"
 namespace qrb200 {
 
 // ------------------------------------------------------------------ single tile tasks
@@ -732,6 +757,7 @@ struct b200qr_plan_s {
     int2 *d_sweep_tab = nullptr;
     long long *d_trace_off = nullptr;
     float *d_tauc = nullptr;
+    float *d_W = nullptr;                    // variant 5: m x (6*K*32) workspace, six blocks (V, T, V^T: hi and lo), tile (i,k) like A
     std::vector<long long> trace_off;
     unsigned long long watchdog_ns;
 };
@@ -769,19 +795,21 @@ static int make_tile_map(CUtensorMap *map, float *dA, int m, int n, int ldm, boo
     return r == CUDA_SUCCESS ? B200QR_OK : B200QR_ECUDA;
 }
 
-// kernel variants: 1 / 2 = SIMT sweeps with 1 / 2 matrix columns per consumer thread, 3 = tensor-core sweeps
-static const void *kernel_of(int nc)
+// kernel variants: 1 / 2 = SIMT sweeps with 1 / 2 matrix columns per consumer thread, 3 / 4 / 5 = tensor-core sweeps
+static const void *kernel_of(int nc, bool prof = false)
 {
+    if (nc == 5) return prof ? (const void *)tiledqr_persistent_tc3_prof : (const void *)tiledqr_persistent_tc3;
     return nc == 4 ? (const void *)tiledqr_persistent_tc2
                    : (nc == 3 ? (const void *)tiledqr_persistent_tc
                               : (nc == 2 ? (const void *)tiledqr_persistent<2> : (const void *)tiledqr_persistent<1>));
 }
 static int smem_of(int nc)
 {
+    if (nc == 5) return Cfg<5>::SMEM_BYTES;
     return nc == 4 ? Cfg<4>::SMEM_BYTES : (nc == 3 ? Cfg<3>::SMEM_BYTES : (nc == 2 ? Cfg<2>::SMEM_BYTES : Cfg<1>::SMEM_BYTES));
 }
-static int threads_of(int nc) { return nc == 4 ? tc2::NTHREADS_TC2 : (nc == 3 ? tc::NTHREADS_TC : NTHREADS); }
-static int group_of(int nc) { return nc == 4 ? Cfg<4>::G : (nc == 3 ? Cfg<3>::G : CW * nc); }
+static int threads_of(int nc) { return nc == 5 ? tc3::NTHREADS_TC3 : nc == 4 ? tc2::NTHREADS_TC2 : (nc == 3 ? tc::NTHREADS_TC : NTHREADS); }
+static int group_of(int nc) { return nc == 5 ? Cfg<5>::G : nc == 4 ? Cfg<4>::G : (nc == 3 ? Cfg<3>::G : CW * nc); }
 constexpr int CTR_INTS = 64 + 512;     // tickets / trace / SM claim words of the 2-CTA-per-SM engine
 
 extern "C" {
@@ -836,10 +864,12 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
     int dev = 0, sms = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    for (int nc = 1; nc <= 4; ++nc) {
+    for (int nc = 1; nc <= 5; ++nc) {
         CK(cudaFuncSetAttribute(kernel_of(nc), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(nc)));
         CK(cudaFuncSetAttribute(kernel_of(nc), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     }
+    CK(cudaFuncSetAttribute(kernel_of(5, true), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(5)));
+    CK(cudaFuncSetAttribute(kernel_of(5, true), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel_of(3), threads_of(3), smem_of(3)));
     if (occ < 1) return B200QR_EINVAL;
@@ -880,9 +910,11 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
         return B200QR_EINVAL;                      // cannot honour the world-wide variant on this grid
     }
     // tensor-core sweeps (opt-in while they are being validated): same role split, 8 tile columns per sweep
-    if (pl->nc == 2 && getenv("QRB200_TC") && atoi(getenv("QRB200_TC")) != 0)
-        pl->nc = atoi(getenv("QRB200_TC")) == 2 && world == 1 && nvirt == 1 ? 4 : 3;
-    if (pl->nc == 4) {
+    if (pl->nc == 2 && getenv("QRB200_TC") && atoi(getenv("QRB200_TC")) != 0) {
+        const int tcv = atoi(getenv("QRB200_TC"));
+        pl->nc = (tcv == 2 || tcv == 3) && world == 1 && nvirt == 1 ? tcv + 2 : 3;
+    }
+    if (pl->nc >= 4) {
         // one CTA per SM holding two sweep engines; a panel CTA runs four panel warps
         int want = (pl->npanel_ctas * NPW + tc2::NPW4 - 1) / tc2::NPW4;
         if (const char *e = getenv("QRB200_NP")) { int v = *e ? atoi(e) : -1; if (v > 0 && v < grid) want = v; }
@@ -891,12 +923,12 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
     const int G = group_of(pl->nc);
     pl->G = G;
     pl->la_enable = 0;
-    if (const char *e = getenv("QRB200_LOOKAHEAD")) pl->la_enable = atoi(e) != 0;
+    if (const char *e = getenv("QRB200_LOOKAHEAD")) pl->la_enable = atoi(e) != 0 && pl->nc != 5;
 
     // this rank's tickets: sweeps of its blocks in the global skewed order, panels of its tile columns
     // skew of the sweep order: a tensor-core sweep row is several times faster than a TSQRT of the panel
     // chain, so its panel needs a longer head start than one distribution block of steps
-    int skew = pl->nc == 4 ? 32 : G;
+    int skew = pl->nc >= 4 ? 32 : G;
     if (const char *e = getenv("QRB200_SKEW")) { int v = atoi(e); if (v > 0) skew = v; }
     long npan = 0;
     const long ns = b200qr_sched_rank_tickets_skew(p, q, G, skew, rank, world, nullptr, 0, nullptr, 0, &npan);
@@ -907,8 +939,8 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
     pl->nsweeps = (int)ns;
     pl->npanels = (int)npan;
     const int useful = (pl->nsweeps > pl->npanels ? pl->nsweeps : pl->npanels) + pl->npanel_ctas;
-    if (pl->nc != 4 && grid > useful) grid = useful > 0 ? useful : 1;
-    if (pl->nc != 4 && pl->npanel_ctas >= grid) pl->npanel_ctas = grid > 1 ? grid / 2 : 0;
+    if (pl->nc < 4 && grid > useful) grid = useful > 0 ? useful : 1;
+    if (pl->nc < 4 && pl->npanel_ctas >= grid) pl->npanel_ctas = grid > 1 ? grid / 2 : 0;
     if (pl->npanel_ctas == 0) {
         if (pl->nc == 2 && world > 1) return B200QR_EINVAL;
         pl->nc = 1;
@@ -924,6 +956,10 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
     CK(cudaMalloc(&pl->d_tauc, sizeof(float) * (size_t)K * p * TB));
     CK(cudaMemset(pl->d_tauc, 0, sizeof(float) * (size_t)K * p * TB));
     CK(cudaMemset(pl->d_prog, 0, sizeof(int) * (size_t)p * q));
+    if (pl->nc == 5) {
+        const size_t wbytes = sizeof(float) * (size_t)m * K * TB * 6;
+        if (cudaMalloc(&pl->d_W, wbytes) != cudaSuccess) return B200QR_ENOMEM;
+    }
     if (pl->trace && pl->trace != 3) {
         CK(cudaMalloc(&pl->d_trace, sizeof(int) * 2 * (size_t)tiles));
         CK(cudaMalloc(&pl->d_trace_off, sizeof(long long) * K));
@@ -938,6 +974,7 @@ static void plan_free(b200qr_plan_s *pl)
 {
     cudaFree(pl->d_prog); cudaFree(pl->d_ctr); cudaFree(pl->d_sweep_tab); cudaFree(pl->d_panel_tab); cudaFree(pl->d_tauc);
     cudaFree(pl->d_trace); cudaFree(pl->d_trace_off);
+    cudaFree(pl->d_W);
 }
 
 // Fills one rank slot of the kernel arguments (dA/ldm = this rank's matrix).
@@ -961,6 +998,10 @@ static int fill_rank_ctx(RankCtx *rc, b200qr_plan_s *pl, float *dA, int ldm)
         if (!src) return B200QR_EINVAL;            // peers not connected
         rc_ = make_tile_map(&rc->mapV[r], src, pl->m, pl->n, ld, pl->nc >= 3);   // tensor-core operands are swizzled
     }
+    if (pl->nc == 5 && rc_ == B200QR_OK) {
+        rc_ = make_tile_map(&rc->mapW, pl->d_W, pl->m, 6 * pl->K * TB, pl->m, true);
+        rc->wcols = pl->K * TB;
+    }
     return rc_;
 }
 
@@ -975,7 +1016,7 @@ static int reset_progress(b200qr_plan_s *pl, cudaStream_t stream)
 static int launch(KernelArgs *ka, int nc, int grid, cudaStream_t stream)
 {
     void *args[] = {ka};
-    CK(cudaLaunchCooperativeKernel(kernel_of(nc), dim3(grid), dim3(threads_of(nc)), args, smem_of(nc), stream));
+    CK(cudaLaunchCooperativeKernel(kernel_of(nc, ka->rc[0].P.trace_mode == 3), dim3(grid), dim3(threads_of(nc)), args, smem_of(nc), stream));
     return B200QR_OK;
 }
 
@@ -1001,7 +1042,7 @@ int b200qr_plan_grid(b200qr_plan_t pl) { return pl ? pl->grid : B200QR_EINVAL; }
 int b200qr_plan_variant(b200qr_plan_t pl) { return pl ? pl->nc : B200QR_EINVAL; }
 int b200qr_plan_debug_counters(b200qr_plan_t pl, unsigned long long *out, int n)
 {
-    if (!pl || !out || n < 1 || n > 8) return B200QR_EINVAL;
+    if (!pl || !out || n < 1 || n > 32) return B200QR_EINVAL;
     CK(cudaMemcpy(out, pl->d_ctr + 32, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost));
     return B200QR_OK;
 }

@@ -34,6 +34,7 @@ struct Cfg<3> {
     static constexpr int OFF_PANEL = 0;                                         // role split only: overlays the stages
     static constexpr int OFF_BAR = SWEEP_END;
     static constexpr int SMEM_BYTES = OFF_BAR + 512;
+    static constexpr bool BUILD_T = false;
 };
 
 namespace tc {

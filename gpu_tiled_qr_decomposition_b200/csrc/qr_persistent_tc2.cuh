@@ -35,6 +35,7 @@ struct Cfg<4> {
     static constexpr int OFF_PANEL = 0;                                         // panel CTAs never run sweeps
     static constexpr int OFF_BAR = 2 * ENGINE_BYTES;                            // panel warps' barriers (run_panel)
     static constexpr int SMEM_BYTES = OFF_BAR + 256;
+    static constexpr bool BUILD_T = false;
 };
 
 namespace tc2 {

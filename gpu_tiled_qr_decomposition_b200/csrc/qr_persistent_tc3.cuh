@@ -1,0 +1,64 @@
+// qr_persistent_tc3.cuh -- third tensor-core sweep engine (QRB200_TC=3), included by qr_persistent.cu.
+//
+// Same mathematics as the other two tensor-core engines -- the reference's TSMQR / UNMQR
+// (qrdecomp.c:620-644, 736-762) in compact-WY form, every product 3xTF32 on tcgen05 with fp32
+// accumulation in tensor memory -- rebuilt around what the first two measured: a tile row of a sweep
+// is a CHAIN through the resident tile row k (c_top), and the only way to make the chain short is to
+// take everything else off it.  For a block of 32 reflectors (V, T) and 128 matrix columns:
+//     Y = C_bot^T V                  off the chain, issued rows ahead                (issuer A)
+//     S = c_top + Y                  per thread                                        (chain warps)
+//     W = S T                        tcgen05.mma, K = 32                               (issuer B)
+//     c_top -= W                     per thread                                        (chain warps)
+//     C_bot^T -= W V^T               off the chain: accumulator preloaded with C_bot^T (issuer B)
+// so one chain step is: TMEM load, 32 adds, split, TMEM store, 12 small MMAs.  T is NOT rebuilt by
+// every sweep: the panel warp that factors a tile also emits its T factor and the transposed block V^T
+// (build_t_warp, qr_device.cuh) into two workspace matrices with the layout of A, and the sweeps
+// TMA-load them next to V.  Warp roles of a sweep CTA (12 warps, one CTA per SM: 168 registers per thread):
+//     loader   polls the progress words, TMA-loads the row's 4 tiles into the C ring (8 stages) and
+//              V, T, V^T into the operand ring (4 stages)
+//     bulk x4  thread = matrix column: preloads the product-3 accumulator with the column and writes
+//              its hi / lo halves as the A operand of product 1 (all in tensor memory, 3 buffers);
+//              three rows later reads the finished column back into the C stage
+//     chain x4 thread = matrix column: the chain above; c_top stays in registers
+//     storer   TMA-stores finished rows (two stores in flight), publishes their progress words
+//     issuer A splits the operand tiles into hi / lo TF32 halves and issues product 1; issuer B issues
+//              products 2 and 3 (one thread each issues the MMAs)
+// Panel chains run in CTAs of their own (four panel warps each), as in engine 2.
+#pragma once
+#include "qr_umma.cuh"
+
+namespace qrb200 {
+
+template <>
+struct Cfg<5> {
+    static constexpr int G = 4;
+    static constexpr int NS = 3;                                   // only places the panel warps' barriers (run_panel)
+    static constexpr int NCS = 8;                                  // C ring: one tile row of the sweep per stage
+    static constexpr int NOS = 4;                                  // operand ring
+    static constexpr int CSTAGE_BYTES = G * TILE_BYTES;
+    static constexpr int OSTAGE_BYTES = 6 * TILE_BYTES;            // V, T, V^T: hi and lo halves, split by the panel warp
+    static constexpr int OFF_OPS = NCS * CSTAGE_BYTES;
+    static constexpr int SWEEP_END = OFF_OPS + NOS * OSTAGE_BYTES;
+    static constexpr int PANEL_BYTES = 11 * TILE_BYTES + 5120;     // in 2, out 2, R / scratch, six operand tiles, Gram scratch
+    static constexpr int OFF_PANEL = 0;                            // panel CTAs never run sweeps
+    static constexpr int OFF_BAR = SWEEP_END;
+    static constexpr int SMEM_BYTES = OFF_BAR + 1024;
+    static constexpr bool BUILD_T = true;
+};
+
+#define TC3_NS tc3
+#define TC3_PROF 0
+#define TC3_KERNEL tiledqr_persistent_tc3
+#include "qr_persistent_tc3_body.inc"
+#undef TC3_NS
+#undef TC3_PROF
+#undef TC3_KERNEL
+#define TC3_NS tc3p
+#define TC3_PROF 1
+#define TC3_KERNEL tiledqr_persistent_tc3_prof
+#include "qr_persistent_tc3_body.inc"
+#undef TC3_NS
+#undef TC3_PROF
+#undef TC3_KERNEL
+
+}  // namespace qrb200

@@ -191,3 +191,78 @@ extern "C" int b200qr_probe_umma_mode(const float *hA, const float *hV, const fl
     cudaFree(dA); cudaFree(dV); cudaFree(dW); cudaFree(dZ); cudaFree(dD);
     return rc;
 }
+
+// ---- issue-rate probe: cycles per tcgen05.mma (kind::tf32, M = 128, A in tensor memory, K = 8) as a function of N,
+// for one accumulator (dependent accumulation) and for NACC accumulators used round-robin.  One CTA, one issuing thread.
+namespace qrb200 {
+__global__ void __launch_bounds__(128) umma_rate_kernel(long long *out, int reps)
+{
+    extern __shared__ __align__(1024) unsigned char rsm[];
+    __shared__ uint64_t bar_done;
+    __shared__ uint32_t slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 32 * 1024 / 4; i += 128) reinterpret_cast<float *>(rsm)[i] = 0.f;
+    if (tid == 0) { mbar_init(&bar_done, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) tmem_alloc<512>(&slot);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = __reduce_max_sync(FULL, slot);
+    {   // define the A operand region (columns 448..511)
+        float z[TB];
+#pragma unroll
+        for (int i = 0; i < TB; ++i) z[i] = 0.f;
+        tmem_st_32x32(tmem + ((uint32_t)(warp * 32) << 16) + 448, z);
+        tmem_st_32x32(tmem + ((uint32_t)(warp * 32) << 16) + 480, z);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t bdesc = ((smem_u32(rsm) >> 4) & 0x3fff) | (1u << 16);
+    uint32_t phase = 0;
+    int slot_out = 0;
+    const int Ns[4] = {32, 64, 128, 256};
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+        for (int nacc = 1; nacc <= 2; ++nacc) {
+            if (Ns[ni] * nacc > 384) { if (tid == 0) out[slot_out] = 0; ++slot_out; continue; }
+            const uint32_t idesc = umma_idesc_tf32(128, Ns[ni], false, false);
+            long long t0 = 0;
+            if (tid == 0) {
+                t0 = clock64();
+                for (int r = 0; r < reps; ++r) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_tf32_ts(tmem + (uint32_t)(((r * 4 + kk) % nacc) * Ns[ni]), tmem + 448 + 8 * kk, umma_desc_from(bdesc + 2 * kk), idesc,
+                                     true);
+                }
+                umma_commit(&bar_done);
+            }
+            mbar_wait(&bar_done, phase);
+            phase ^= 1;
+            if (tid == 0) out[slot_out] = clock64() - t0;
+            ++slot_out;
+            __syncthreads();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+}  // namespace qrb200
+
+// out8: cycles for reps*4 MMAs: N = 32 (1 acc, 2 acc), 64 (1, 2), 128 (1, 2), 256 (1, -)
+extern "C" int b200qr_probe_umma_rate(long long *out8, int reps)
+{
+    if (!out8 || reps <= 0) return B200QR_EINVAL;
+    long long *d = nullptr;
+    if (cudaMalloc(&d, 8 * sizeof(long long)) != cudaSuccess) return B200QR_ECUDA;
+    cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 33 * 1024);
+    umma_rate_kernel<<<1, 128, 33 * 1024>>>(d, reps);
+    int rc = cudaDeviceSynchronize() == cudaSuccess ? B200QR_OK : B200QR_ECUDA;
+    if (rc == B200QR_OK) cudaMemcpy(out8, d, 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return rc;
+}

@@ -80,6 +80,7 @@ int         b200qr_probe_panel(long long *cycles4, int reps);
  * hW 128 x 32 row-major or NULL; hZ <- A^T V (128 x 32 row-major, 3xTF32 on the tensor cores);
  * hD2 <- A^T - W V^T when hW is given. */
 int         b200qr_probe_umma(const float *hA, const float *hV, const float *hW, float *hZ, float *hD2);
+int         b200qr_probe_umma_rate(long long *out8, int reps);   /* cycles of reps*4 tcgen05.mma (tf32, M=128, K=8): N=32,64,128,256 x {1,2} accumulators */
 
 /* ---- plan: workspace + schedule for one (m, n) shape ----------------------------
  * Replaces the per-call cudaMalloc of task grid / queue / tau in cudaQRTask

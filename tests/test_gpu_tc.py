@@ -1,4 +1,4 @@
-"""Tensor-core sweep engine (csrc/qr_persistent_tc.cuh, QRB200_TC=1): same factorisation, the
+"""Tensor-core sweep engines (csrc/qr_persistent_tc*.cuh, QRB200_TC=1, 2, 3): same factorisation, the
 trailing update runs as 3xTF32 tcgen05 products.  Stated tolerance: elementwise within
 5e-4 * max|R| of the oracle (3xTF32 keeps ~2^-21 per product instead of 2^-24), backward error
 and orthogonality <= 10 in units of n*eps (SURVEY 8c's bound for the 3xTF32 path)."""
@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 EPS = float(np.finfo(np.float32).eps)
 
 
-@pytest.fixture(params=["1", "2"])
+@pytest.fixture(params=["1", "2", "3"])
 def tc_env(request):
     old = os.environ.get("QRB200_TC")
     os.environ["QRB200_TC"] = request.param
@@ -29,7 +29,7 @@ def test_tc_sweeps_match_oracle(cuda, qr, po, tc_env, m, n):
     d = torch.from_numpy(a).cuda()
     dt = torch.zeros_like(d)
     plan = qr.Plan(m, n)
-    assert plan.variant == {"1": 3, "2": 4}[os.environ["QRB200_TC"]]
+    assert plan.variant == {"1": 3, "2": 4, "3": 5}[os.environ["QRB200_TC"]]
     s = torch.cuda.current_stream().cuda_stream
     plan.factor(d.data_ptr(), m, s)
     plan.tau_to_reference(dt.data_ptr(), m, s)
