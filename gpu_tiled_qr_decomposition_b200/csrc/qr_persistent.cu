@@ -101,8 +101,10 @@ struct RankCtx {
     Params P;
     CUtensorMap mapA;               // this rank's matrix, 128B-swizzled tiles (thread-per-column access)
     CUtensorMap mapV[MAXW];         // every rank's matrix, dense tiles (reflector tiles, broadcast reads)
-    CUtensorMap mapW;               // tensor-core engine 3: workspace of pre-split operand tiles (six column blocks)
-    int wcols;                      // columns per block of that workspace (K * 32)
+    CUtensorMap mapW;               // tensor-core engine 3: workspace of pre-split operand tiles, box = the six tiles of one (i, k)
+    CUtensorMap mapA4;              // tensor-core engine 3: this rank's matrix, box = one tile row of a sweep (4 tiles)
+    CUtensorMap mapW2;              // tensor-core engine 3: the operand workspace, box = one operand (hi and lo tile)
+    int wcols;                      // (unused)
 };
 struct alignas(64) KernelArgs {
     int nvirt;                      // ranks emulated by this launch: CTA b works for rank slot b % nvirt
@@ -195,9 +197,8 @@ __device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int p
     // BUILD_T (no look-ahead there): the slots behind the broadcast area stage the six operand tiles and the Gram
     // scratch of build_t_warp (PANEL_BYTES of that configuration has room for seven tiles there)
     float *opstage = ptop, *gscratch = ptop + 6 * TB * TB;
-    auto store_ops = [&](int row) {                  // lane 0: the six operand tiles -> workspace column blocks
-#pragma unroll
-        for (int w = 0; w < 6; ++w) tma_store_2d(mapW, row * TB, w * wcols + k * TB, opstage + w * TB * TB);
+    auto store_ops = [&](int row) {                  // lane 0: the six operand tiles -> workspace columns k*192 ..
+        tma_store_2d(mapW, row * TB, k * 6 * TB, opstage);       // one box: the six tiles are adjacent in the stage and in the workspace
     };
     uint64_t *pfull = reinterpret_cast<uint64_t *>(g_smem + C::OFF_BAR) + 3 * C::NS + 2 * pw;
     int *prog_col = P.prog + (size_t)k * p;
@@ -782,13 +783,13 @@ static tmap_encode_fn tmap_encoder()
 
 // 2-D map over the column-major matrix: dim0 = rows (contiguous), dim1 = columns (ldm apart);
 // box = one 32x32 tile.
-static int make_tile_map(CUtensorMap *map, float *dA, int m, int n, int ldm, bool swizzle)
+static int make_tile_map(CUtensorMap *map, float *dA, int m, int n, int ldm, bool swizzle, int box_cols = TB)
 {
     tmap_encode_fn enc = tmap_encoder();
     if (!enc) return B200QR_ECUDA;
     cuuint64_t dims[2] = {(cuuint64_t)m, (cuuint64_t)n};
     cuuint64_t strides[1] = {(cuuint64_t)ldm * sizeof(float)};
-    cuuint32_t box[2] = {TB, TB}, estr[2] = {1, 1};
+    cuuint32_t box[2] = {TB, (cuuint32_t)box_cols}, estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dA, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -999,8 +1000,10 @@ static int fill_rank_ctx(RankCtx *rc, b200qr_plan_s *pl, float *dA, int ldm)
         rc_ = make_tile_map(&rc->mapV[r], src, pl->m, pl->n, ld, pl->nc >= 3);   // tensor-core operands are swizzled
     }
     if (pl->nc == 5 && rc_ == B200QR_OK) {
-        rc_ = make_tile_map(&rc->mapW, pl->d_W, pl->m, 6 * pl->K * TB, pl->m, true);
-        rc->wcols = pl->K * TB;
+        rc_ = make_tile_map(&rc->mapW, pl->d_W, pl->m, 6 * pl->K * TB, pl->m, true, 6 * TB);
+        if (rc_ == B200QR_OK) rc_ = make_tile_map(&rc->mapA4, dA, pl->m, pl->n, ldm, true, 4 * TB);
+        if (rc_ == B200QR_OK) rc_ = make_tile_map(&rc->mapW2, pl->d_W, pl->m, 6 * pl->K * TB, pl->m, true, 2 * TB);
+        rc->wcols = 0;
     }
     return rc_;
 }

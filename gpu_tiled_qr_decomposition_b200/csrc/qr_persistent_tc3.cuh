@@ -33,12 +33,16 @@ template <>
 struct Cfg<5> {
     static constexpr int G = 4;
     static constexpr int NS = 3;                                   // only places the panel warps' barriers (run_panel)
-    static constexpr int NCS = 8;                                  // C ring: one tile row of the sweep per stage
-    static constexpr int NOS = 4;                                  // operand ring
+    static constexpr int NCI = 3;                                  // IN ring: a tile row of the sweep as loaded
+    static constexpr int NCO = 5;                                  // OUT ring: a finished tile row for the storer
+    static constexpr int NOS = 4;                                  // operand rings (V, T, V^T: hi and lo tile each)
     static constexpr int CSTAGE_BYTES = G * TILE_BYTES;
-    static constexpr int OSTAGE_BYTES = 6 * TILE_BYTES;            // V, T, V^T: hi and lo halves, split by the panel warp
-    static constexpr int OFF_OPS = NCS * CSTAGE_BYTES;
-    static constexpr int SWEEP_END = OFF_OPS + NOS * OSTAGE_BYTES;
+    static constexpr int OSTAGE_BYTES = 2 * TILE_BYTES;
+    static constexpr int OFF_OUT = NCI * CSTAGE_BYTES;
+    static constexpr int OFF_V = OFF_OUT + NCO * CSTAGE_BYTES;
+    static constexpr int OFF_T = OFF_V + NOS * OSTAGE_BYTES;
+    static constexpr int OFF_X = OFF_T + NOS * OSTAGE_BYTES;
+    static constexpr int SWEEP_END = OFF_X + NOS * OSTAGE_BYTES;
     static constexpr int PANEL_BYTES = 11 * TILE_BYTES + 5120;     // in 2, out 2, R / scratch, six operand tiles, Gram scratch
     static constexpr int OFF_PANEL = 0;                            // panel CTAs never run sweeps
     static constexpr int OFF_BAR = SWEEP_END;

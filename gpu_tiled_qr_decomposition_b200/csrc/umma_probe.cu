@@ -108,6 +108,26 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(const __grid_constant__
             const float *A2[3] = {sm.w_hi, sm.w_hi, sm.w_lo};
             const float *B2[3] = {sm.vt_hi, sm.vt_lo, sm.vt_hi};
             bool acc2 = false;
+            if (mode & 8) {
+                // B operand = the reflector tile itself described as MN-major (N = tile rows contiguous in a 128-byte line,
+                // K = reflector index: one 1024-byte swizzle atom per K = 8 step).  (mode >> 4) & 7 picks the LBO / SBO variant.
+                const uint32_t idesc_mn = umma_idesc_tf32(128, 32, false, true);
+                const float *BM[3] = {sm.v_hi, sm.v_lo, sm.v_hi};
+                const int var = (mode >> 4) & 7;
+                const uint64_t lbo = (var == 0) ? 1 : ((var == 3) ? (4096 >> 4) : (1024 >> 4));
+                const uint64_t sbo = (var == 2) ? 1 : (1024 >> 4);
+                for (int pass = 0; pass < 3; ++pass)
+                    for (int kk = 0; kk < 4; ++kk) {
+                        uint64_t d = 0;
+                        d |= (uint64_t)(((smem_u32(BM[pass]) + kk * 1024) >> 4) & 0x3fff);
+                        d |= lbo << 16;
+                        d |= sbo << 32;
+                        d |= (uint64_t)1 << 46;
+                        d |= (uint64_t)2 << 61;
+                        umma_tf32(tmem + 32, umma_desc_sw128(A2[pass], kk * 32), d, idesc_mn, acc2);
+                        acc2 = true;
+                    }
+            } else
             for (int pass = 0; pass < 3; ++pass)
                 for (int kk = 0; kk < 4; ++kk) {
                     umma_tf32(tmem + 32, umma_desc_sw128(A2[pass], kk * 32), umma_desc_sw128(B2[pass], kk * 32), idesc2, acc2);

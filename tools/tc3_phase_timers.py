@@ -21,10 +21,10 @@ us = lambda x: x / rows / 1965.0   # SM cycles at 1965 MHz -> us
 print("variant", plan.variant, "grid", plan.grid, "kernel ms %.2f" % e0.elapsed_time(e1), "rows (all CTAs)", rows)
 print("per row (us): chain total %.2f | waits: YR %.2f WR %.2f PR(prev) %.2f -> chain compute %.2f" % (
     us(v[0]), us(v[1]), us(v[2]), us(v[3]), us(v[0] - v[1] - v[2] - v[3])))
-print("  loader: total %.2f | CE %.2f OE %.2f poll %.2f threadfence %.2f fence.proxy %.2f" % (us(v[8]), us(v[5]), us(v[6]), us(v[7]), us(v[18]), us(v[19])))
-print("  pre: CF %.2f PF %.2f | post: PR %.2f | storer: CC %.2f wait_group %.2f retire %.2f" % (us(v[9]), us(v[10]), us(v[11]), us(v[12]), us(v[13]), us(v[20])))
-print("  issuer A: OF %.2f PS %.2f | issuer B: SR %.2f WS %.2f" % (us(v[14]), us(v[15]), us(v[16]), us(v[17])))
+print("  loader: total %.2f (non-blocking round robin over its four streams)" % us(v[8]))
+print("  pre: CF %.2f PF %.2f | post: PR %.2f OUT-stage %.2f | storer: CC %.2f wait_group %.2f retire %.2f" % (us(v[9]), us(v[10]), us(v[11]), us(v[6]), us(v[12]), us(v[13]), us(v[20])))
+print("  issuer A: VF %.2f PS %.2f | issuer B: SR %.2f WS %.2f" % (us(v[14]), us(v[15]), us(v[16]), us(v[17])))
 print("  chain detail: ld W %.2f  split/st W %.2f  ld Y %.2f  split/st S %.2f  fence+arrive SR %.2f  arrive WS %.2f" % tuple(us(v[i]) for i in range(21, 27)))
 print("  loader batches per row %.2f" % (v[27] / rows))
 print("  issuer A: mma issue %.2f | issuer B: m2 issue %.2f  m3 issue %.2f" % tuple(us(v[i]) for i in range(29, 32)))
-print("  polls %.0f, of which found their row not ready %.0f" % (v[27], v[28]))
+print("  fenced polls %.0f" % v[27])
