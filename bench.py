@@ -164,6 +164,59 @@ def gram_check(torch, d, A0, c0, c1):
     return (torch.linalg.norm(R.t() @ R - G2) / torch.linalg.norm(G2)).item()
 
 
+def roofline_of(variant, achieved_tf, fp32_peak_tf, peaks, peak_src, n, ms_step):
+    """The factorisation is one persistent kernel, so the kernel's roofline is the step's.  Variants 1 / 2 apply the
+    reflectors on the FP32 SIMT pipe (bound: the FFMA rate, measured in this process).  Variant 5 runs the trailing
+    update as 3xTF32 tcgen05 products: the bound is the tensor pipe at a sixth of the measured dense bf16 rate (TF32
+    runs at half the bf16 rate, three passes per product); the fraction of the FP32 SIMT peak -- the north-star's
+    '% of B200 peak for the working precision' -- is reported next to it."""
+    common = {"achieved": achieved_tf, "unit": "TFLOP/s", "traffic": None,
+              "frac_of_fp32_simt_peak": achieved_tf / fp32_peak_tf, "fp32_simt_peak": fp32_peak_tf,
+              "frac_of_bf16_tensor_peak": achieved_tf / peaks["bf16_tflops"],
+              "hbm_algorithmic_gbs": 8.0 * n * n / (ms_step * 1e-3) * 1e-9}
+    if variant == 5:
+        peak = peaks["bf16_tflops"] / 6.0
+        common.update({"bound": "tensor", "peak": peak, "frac": achieved_tf / peak,
+                       "kernel": "tiledqr_persistent_tc3 (the only kernel of a step)",
+                       "peak_source": "%s bf16_tflops / 6 (3xTF32: TF32 at half the bf16 rate, three passes); FP32 SIMT "
+                                      "peak from the FFMA microbench run in this process" % peak_src})
+    else:
+        common.update({"bound": "fp32-simt", "peak": fp32_peak_tf, "frac": achieved_tf / fp32_peak_tf,
+                       "kernel": "tiledqr_persistent (the only kernel of a step)",
+                       "peak_source": "FFMA microbench run in this process (b200qr_measure_fp32_peak); %s carries "
+                                      "only HBM and bf16-tensor peaks" % peak_src})
+    return common
+
+
+def north_star_run(torch, q, n, fp32_peak_tf, peaks, peak_src):
+    """One warm-up and two timed factorisations of an n x n matrix (BASELINE.json's 32768 target on one GPU)."""
+    flops = qr_flops(n, n)
+    stream = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device="cuda").manual_seed(6)
+    A0 = torch.rand((n, n), generator=g, device="cuda", dtype=torch.float32) * 2 - 1
+    d = torch.empty_like(A0)
+    plan = q.Plan(n, n)
+    best = None
+    for it in range(3):
+        d.copy_(A0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        plan.factor(d.data_ptr(), n, stream)
+        e1.record()
+        torch.cuda.synchronize()
+        if it > 0:
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+    tf = flops / (best * 1e-3) * 1e-12
+    out = {"workload": "%dx%d square tiled QR, tile size 32, 1 GPU" % (n, n), "ms": best, "value": tf * 1e3, "unit": "GFLOP/s",
+           "kernel_variant": plan.variant, "gram_rel_err": gram_check(torch, d, A0, 0, 1024),
+           "roofline": roofline_of(plan.variant, tf, fp32_peak_tf, peaks, peak_src, n, best)}
+    plan.close()
+    del A0, d
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200_single(args):
     import torch
     import gpu_tiled_qr_decomposition_b200 as q
@@ -219,13 +272,14 @@ def run_b200_single(args):
     fp32 = C.c_double(0)
     q.check(L.b200qr_measure_fp32_peak(C.byref(fp32), 20000))
     achieved_tf = flops / (ms_step * 1e-3) * 1e-12
-    roofline = {"bound": "fp32-simt", "achieved": achieved_tf, "peak": fp32.value * 1e-3, "unit": "TFLOP/s",
-                "frac": achieved_tf / (fp32.value * 1e-3), "traffic": None,
-                "kernel": "tiledqr_persistent (the only kernel of a step)",
-                "peak_source": "FFMA microbench run in this process (b200qr_measure_fp32_peak); %s carries "
-                               "only HBM and bf16-tensor peaks" % peak_src,
-                "frac_of_bf16_tensor_peak": achieved_tf / peaks["bf16_tflops"],
-                "hbm_algorithmic_gbs": 8.0 * n * n / (ms_step * 1e-3) * 1e-9}
+    roofline = roofline_of(plan.variant, achieved_tf, fp32.value * 1e-3, peaks, peak_src, n, ms_step)
+    # the north-star configuration (32768 x 32768 on one GPU), one extra factorisation: reported next to the headline
+    north = None
+    if args.north_size and args.north_size != n:
+        try:
+            north = north_star_run(torch, q, args.north_size, fp32.value * 1e-3, peaks, peak_src)
+        except Exception as e:                                    # e.g. not enough free memory on a shared box
+            north = {"skipped": str(e)[:200]}
     sec, kind, cores = cpu_reference_run(args.cpu_sample, reps=1)
     cpu = {"value": qr_flops(args.cpu_sample, args.cpu_sample) / sec * 1e-9, "unit": "GFLOP/s", "cores": cores,
            "kind": kind, "sample": "%dx%d RANDZO matrix, b=32, one run of taskQRP_threads (%.1f s), "
@@ -245,6 +299,8 @@ def run_b200_single(args):
                     "host memory (workspace cached between calls of one shape)", "steps": e2e_steps,
                     "max_abs_diff_vs_device_path": e2e_err},
             "gpu_launches": args.steps * 1, "clocks": clocks, "check": {"gram_rel_err": gram}}
+    if north is not None:
+        line["north_star_32768"] = north
     print(json.dumps(line), flush=True)
     plan.close()
 
@@ -391,6 +447,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=8192)
+    ap.add_argument("--north-size", type=int, default=32768,
+                    help="N = 1: also factor this size once (BASELINE.json's 32768 target) and report it; 0 = skip")
     ap.add_argument("--cpu-sample", type=int, default=4096, help="CPU baseline sample size (square)")
     ap.add_argument("--ref-size", type=int, default=0)
     ap.add_argument("--multi-size", type=int, default=32768, help="matrix size of the N > 1 (block-cyclic) workload")

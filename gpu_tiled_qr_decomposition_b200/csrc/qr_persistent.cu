@@ -910,10 +910,20 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
     } else if (pl->nc == 2 && grid < 16) {
         return B200QR_EINVAL;                      // cannot honour the world-wide variant on this grid
     }
-    // tensor-core sweeps (opt-in while they are being validated): same role split, 8 tile columns per sweep
-    if (pl->nc == 2 && getenv("QRB200_TC") && atoi(getenv("QRB200_TC")) != 0) {
-        const int tcv = atoi(getenv("QRB200_TC"));
-        pl->nc = (tcv == 2 || tcv == 3) && world == 1 && nvirt == 1 ? tcv + 2 : 3;
+    // Tensor-core sweeps.  QRB200_TC = 1 / 2 / 3 forces one of the three engines (1, 2: earlier designs kept for
+    // comparison), QRB200_TC = 0 forces the SIMT engine.  Unset: engine 3 on one GPU once the matrix is large enough for
+    // its faster tile rows to outweigh its slower panel chain (measured on B200: 8192^2 SIMT 25.5 ms / engine 3 29.3 ms,
+    // 16384^2 178 / 149 ms, 32768^2 1358 / 1168 ms) and its operand workspace (six times the factored columns) fits.
+    if (pl->nc == 2) {
+        const char *e = getenv("QRB200_TC");
+        if (e && *e) {
+            const int tcv = atoi(e);
+            if (tcv != 0) pl->nc = (tcv == 2 || tcv == 3) && world == 1 && nvirt == 1 ? tcv + 2 : 3;
+        } else if (world == 1 && nvirt == 1 && K >= 384) {
+            size_t free_b = 0, total_b = 0;
+            const size_t wbytes = sizeof(float) * (size_t)m * K * TB * 6;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > wbytes + ((size_t)1 << 30)) pl->nc = 5;
+        }
     }
     if (pl->nc >= 4) {
         // one CTA per SM holding two sweep engines; a panel CTA runs four panel warps

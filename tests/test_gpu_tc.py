@@ -59,3 +59,67 @@ def test_tc_sweeps_match_oracle(cuda, qr, po, tc_env, m, n):
     back = (torch.linalg.norm(RX.t().double() - AX) / (torch.linalg.norm(A.double()) * torch.linalg.norm(Xn.double()) / 8 * n * EPS)).item()
     assert back <= 10.0, back
     plan.close()
+
+
+def _factor(torch, qr, A, n, tc):
+    old = os.environ.get("QRB200_TC")
+    os.environ["QRB200_TC"] = tc
+    try:
+        plan = qr.Plan(n, n)
+        d = A.clone()
+        plan.factor(d.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        return plan, d
+    finally:
+        if old is None:
+            os.environ.pop("QRB200_TC", None)
+        else:
+            os.environ["QRB200_TC"] = old
+
+
+def test_tc3_large_matrix_against_simt_engine(cuda, qr):
+    """Engine 3 (the default above 12288^2) at a size the oracle does not finish in seconds: R must equal the SIMT
+    engine's up to row sign (BASELINE.json's criterion; a pivot close to zero may round to the other sign), within
+    5e-4 * max|R|, and pass the backward-error / orthogonality bounds (<= 10 n eps) through GPU-applied Q."""
+    torch = cuda
+    n = 6144
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = torch.rand((n, n), device="cuda", generator=g) * 2 - 1
+    p_simt, d_simt = _factor(torch, qr, A, n, "0")
+    p_tc, d_tc = _factor(torch, qr, A, n, "3")
+    assert p_simt.variant == 2 and p_tc.variant == 5
+    Rs, Rt = torch.triu(d_simt.t()), torch.triu(d_tc.t())
+    sg = torch.sign((Rs * Rt).sum(dim=1))
+    scale = Rs.abs().max().item()
+    assert int((sg == 0).sum().item()) == 0
+    assert ((Rt - sg[:, None] * Rs).abs().max() / scale).item() <= 5e-4
+    s = torch.cuda.current_stream().cuda_stream
+    X = torch.randn((32, n), device="cuda", generator=g)
+    Y = X.clone()
+    p_tc.apply_q(d_tc.data_ptr(), n, Y.data_ptr(), n, 32, False, s)
+    p_tc.apply_q(d_tc.data_ptr(), n, Y.data_ptr(), n, 32, True, s)
+    torch.cuda.synchronize()
+    orth = (torch.linalg.norm(Y.double() - X.double()) / (torch.linalg.norm(X.double()) * n * EPS)).item()
+    assert orth <= 10.0, orth
+    Xn = torch.randn((32, n), device="cuda", generator=g)
+    RX = (Rt.double() @ Xn.t().double()).float().t().contiguous()
+    p_tc.apply_q(d_tc.data_ptr(), n, RX.data_ptr(), n, 32, False, s)
+    torch.cuda.synchronize()
+    AX = A.t().double() @ Xn.t().double()
+    back = (torch.linalg.norm(RX.t().double() - AX) /
+            (torch.linalg.norm(A.double()) * torch.linalg.norm(Xn.double()) / 32 ** 0.5 * n * EPS)).item()
+    assert back <= 10.0, back
+    p_simt.close(); p_tc.close()
+
+
+def test_default_engine_selection(cuda, qr):
+    """Unset QRB200_TC: SIMT engine up to 8192^2, tensor-core engine 3 from 12288^2 on one GPU."""
+    old = os.environ.pop("QRB200_TC", None)
+    try:
+        for n, want in ((8192, 2), (12288, 5)):
+            plan = qr.Plan(n, n)
+            assert plan.variant == want, (n, plan.variant)
+            plan.close()
+    finally:
+        if old is not None:
+            os.environ["QRB200_TC"] = old
