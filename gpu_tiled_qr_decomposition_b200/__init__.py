@@ -25,7 +25,7 @@ EXPORTS = (
     "b200qr_sched_init", "b200qr_sched_next", "b200qr_sched_done", "b200qr_sched_free",
     "b200qr_sched_progress", "b200qr_sched_ready_count", "b200qr_sched_dep_count",
     "b200qr_sched_predecessors", "b200qr_sched_device_order", "b200qr_sched_sweep_order", "b200qr_sched_rank_tickets", "b200qr_sched_sweep_order_skew",
-    "b200qr_sched_rank_tickets_skew",
+    "b200qr_sched_rank_tickets_skew", "b200qr_sched_sweep_order_lag",
     "b200qr_dist_create", "b200qr_dist_destroy", "b200qr_dist_handle_bytes", "b200qr_dist_export",
     "b200qr_dist_connect", "b200qr_dist_matrix", "b200qr_dist_tau_device", "b200qr_dist_block",
     "b200qr_dist_owner", "b200qr_dist_grid", "b200qr_dist_read_trace", "b200qr_dist_tile_tasks", "b200qr_dist_reset", "b200qr_dist_factor",
@@ -108,6 +108,8 @@ def lib():
         L.b200qr_sched_device_order.restype = C.c_long
         L.b200qr_sched_sweep_order.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.c_long]
         L.b200qr_sched_sweep_order.restype = C.c_long
+        L.b200qr_sched_sweep_order_lag.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_long]
+        L.b200qr_sched_sweep_order_lag.restype = C.c_long
         L.b200qr_sched_rank_tickets.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_long, vp, C.c_long,
                                                 C.POINTER(C.c_long)]
         L.b200qr_sched_rank_tickets.restype = C.c_long

@@ -942,10 +942,16 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
     int skew = pl->nc >= 4 ? 32 : G;
     if (const char *e = getenv("QRB200_SKEW")) { int v = atoi(e); if (v > 0) skew = v; }
     long npan = 0;
-    const long ns = b200qr_sched_rank_tickets_skew(p, q, G, skew, rank, world, nullptr, 0, nullptr, 0, &npan);
+    long ns = b200qr_sched_rank_tickets_skew(p, q, G, skew, rank, world, nullptr, 0, nullptr, 0, &npan);
     if (ns < 0) return B200QR_EINVAL;
     std::vector<int> tab(2 * (size_t)(ns > 0 ? ns : 1)), ptab((size_t)(npan > 0 ? npan : 1));
     b200qr_sched_rank_tickets_skew(p, q, G, skew, rank, world, tab.data(), ns, ptab.data(), npan, &npan);
+    // engine 3 on one GPU: lagged order (sweeps that run together share the step, so its operand tiles stay in L2)
+    if (pl->nc == 5 && world == 1 && !getenv("QRB200_SKEW")) {
+        int lag = 16;
+        if (const char *e = getenv("QRB200_LAG")) { int v = atoi(e); if (v >= 0) lag = v; }
+        if (b200qr_sched_sweep_order_lag(p, q, G, lag, tab.data(), ns) != ns) return B200QR_EINVAL;
+    }
     ptab.resize((size_t)npan);
     pl->nsweeps = (int)ns;
     pl->npanels = (int)npan;

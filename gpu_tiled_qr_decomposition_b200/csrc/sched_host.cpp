@@ -165,6 +165,44 @@ long b200qr_sched_sweep_order_skew(int M, int N, int G, int B, int *out2, long c
     return n;
 }
 
+// Lagged order (tensor-core engine 3).  With four tile columns per sweep the reflector / T operands of a tile row
+// are 1.5x the bytes of the row itself, so sweeps that run at the same time should work on the SAME step k: then the
+// step's operand tiles are read from HBM once and served from L2 to everyone else.  The skewed order above does the
+// opposite (at any time every group is at a different step).  Here a sweep is
+//     far     if its group does not become the diagonal group within the next LAG steps:  key = k + LAG
+//             -- all far sweeps of a step are adjacent in the order, LAG steps behind its panel (which is done by then);
+//     urgent  otherwise:                                                                    key = max(k, kf + LAG)
+//             -- in step order, right behind the panels that need them; kf = G*g - LAG - 2 is the group's last far step,
+//             so the group's own history stays in order (ties keep smaller k first).
+// For a fixed group the key never decreases with k, and P(k) needs S(k-1, diagonal group of k-1) whose key is k-1:
+// a topological order of the macro-task DAG.
+long b200qr_sched_sweep_order_lag(int M, int N, int G, int LAG, int *out2, long cap)
+{
+    if (M <= 0 || N <= 0 || G <= 0 || LAG < 0) return -1;
+    const int K = M < N ? M : N;
+    const int GB = (N + G - 1) / G;
+    auto key = [&](int k, int g) -> long {
+        if (g > (k + LAG + 1) / G) return (long)k + LAG;
+        const long kf = (long)G * g - LAG - 2;
+        return kf >= 0 && kf + LAG > k ? kf + LAG : k;
+    };
+    std::vector<long> count((size_t)K + (size_t)LAG + (size_t)G * GB + 4, 0);
+    long n = 0;
+    for (int k = 0; k < K; ++k) {
+        if (k + 1 >= N) continue;
+        for (int g = (k + 1) / G; g < GB; ++g) { ++count[(size_t)key(k, g) + 1]; ++n; }
+    }
+    for (size_t i = 1; i < count.size(); ++i) count[i] += count[i - 1];
+    for (int k = 0; k < K; ++k) {                       // k ascending => ties keep smaller k first
+        if (k + 1 >= N) continue;
+        for (int g = (k + 1) / G; g < GB; ++g) {
+            long pos = count[(size_t)key(k, g)]++;
+            if (pos < cap) { out2[2 * pos] = k; out2[2 * pos + 1] = g; }
+        }
+    }
+    return n;
+}
+
 // Tickets of one rank of the 1-D block-cyclic distribution (block = G tile columns, block g on
 // rank g % world): the sweeps of its blocks, in the global skewed order, and the panels of its
 // tile columns, ascending.  Every rank's streams are subsequences of the global streams, so the

@@ -209,6 +209,8 @@ int  b200qr_sched_predecessors(const b200qr_task *t, b200qr_task pred[3]);
 long b200qr_sched_sweep_order(int M, int N, int G, int *out2, long cap);
 /* Same with an explicit skew B (key k + B*g; B = G above): any B >= 0 is a topological order.       */
 long b200qr_sched_sweep_order_skew(int M, int N, int G, int B, int *out2, long cap);
+/* Lagged order of the tensor-core engine 3: far sweeps of a step adjacent (key k + LAG), near-diagonal ones in step order. */
+long b200qr_sched_sweep_order_lag(int M, int N, int G, int LAG, int *out2, long cap);
 long b200qr_sched_rank_tickets_skew(int M, int N, int G, int B, int rank, int world, int *sweeps2, long cap, int *panels,
                                     long capp, long *npanels);
 /* Tickets of one rank of the block-cyclic distribution (block g of G tile columns on rank g % world):

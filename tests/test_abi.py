@@ -179,3 +179,24 @@ def test_device_ticket_order_is_a_topological_order(qr, M, N):
         for j in range(n):
             p = (buf[j].type, buf[j].l, buf[j].m, buf[j].k)
             assert pos[p] < i, (p, (ty, l, m, k))
+
+
+def test_lagged_sweep_order_is_topological(qr):
+    """b200qr_sched_sweep_order_lag: same sweeps as the skewed order; for a fixed group steps ascend; every S(k, .) comes
+    after S(k-1, diagonal group of step k-1) -- the sweep P(k) waits for."""
+    import ctypes as C
+    L = qr.lib()
+    for (M, N, G, LAG) in ((24, 24, 4, 6), (40, 28, 4, 16), (16, 33, 4, 0), (64, 64, 4, 16)):
+        n = L.b200qr_sched_sweep_order_lag(M, N, G, LAG, None, 0)
+        assert n == L.b200qr_sched_sweep_order(M, N, G, None, 0)
+        out = np.zeros((n, 2), dtype=np.int32)
+        assert L.b200qr_sched_sweep_order_lag(M, N, G, LAG, out.ctypes.data_as(C.c_void_p), n) == n
+        ref = np.zeros((n, 2), dtype=np.int32)
+        L.b200qr_sched_sweep_order(M, N, G, ref.ctypes.data_as(C.c_void_p), n)
+        assert sorted(map(tuple, out)) == sorted(map(tuple, ref))
+        pos = {tuple(kg): i for i, kg in enumerate(map(tuple, out))}
+        for (k, g), i in pos.items():
+            if (k - 1, g) in pos:
+                assert pos[(k - 1, g)] < i
+            if k >= 1 and (k - 1, k // G) in pos:                  # diagonal group of step k-1 holds tile column k
+                assert pos[(k - 1, k // G)] < i
