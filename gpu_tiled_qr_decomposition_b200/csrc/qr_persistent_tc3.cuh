@@ -13,7 +13,7 @@
 // so one chain step is: TMEM load, 32 adds, split, TMEM store, 12 small MMAs.  T is NOT rebuilt by
 // every sweep: the panel warp that factors a tile also emits its T factor and the transposed block V^T
 // (build_t_warp, qr_device.cuh) into two workspace matrices with the layout of A, and the sweeps
-// TMA-load them next to V.  Warp roles of a sweep CTA (12 warps, one CTA per SM: 168 registers per thread):
+// TMA-load them next to V.  Warp roles of a sweep CTA (13 warps, one CTA per SM):
 //     loader   polls the progress words, TMA-loads the row's 4 tiles into the C ring (8 stages) and
 //              V, T, V^T into the operand ring (4 stages)
 //     bulk x4  thread = matrix column: preloads the product-3 accumulator with the column and writes
@@ -21,8 +21,7 @@
 //              three rows later reads the finished column back into the C stage
 //     chain x4 thread = matrix column: the chain above; c_top stays in registers
 //     storer   TMA-stores finished rows (two stores in flight), publishes their progress words
-//     issuer A splits the operand tiles into hi / lo TF32 halves and issues product 1; issuer B issues
-//              products 2 and 3 (one thread each issues the MMAs)
+//     issuers A / B / C   one thread each issues the MMAs of product 1 / 2 / 3
 // Panel chains run in CTAs of their own (four panel warps each), as in engine 2.
 #pragma once
 #include "qr_umma.cuh"

@@ -273,6 +273,70 @@ __global__ void __launch_bounds__(128) umma_rate_kernel(long long *out, int reps
 }
 }  // namespace qrb200
 
+// Do two issuing threads (different warps, different accumulators) double the tcgen05.mma rate, or is the ~46-cycle
+// floor per instruction a property of the tensor pipe?  out2[0]: cycles for one thread issuing reps*4 MMAs (N = 32);
+// out2[1]: cycles until BOTH of two threads have finished reps*4 MMAs each.
+namespace qrb200 {
+__global__ void __launch_bounds__(128) umma_rate2_kernel(long long *out, int reps)
+{
+    extern __shared__ __align__(1024) unsigned char rsm2[];
+    __shared__ uint64_t bar_done[2];
+    __shared__ uint32_t slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 32 * 1024 / 4; i += 128) reinterpret_cast<float *>(rsm2)[i] = 0.f;
+    if (tid == 0) { mbar_init(&bar_done[0], 1); mbar_init(&bar_done[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) tmem_alloc<512>(&slot);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = __reduce_max_sync(FULL, slot);
+    {
+        float z[TB];
+#pragma unroll
+        for (int i = 0; i < TB; ++i) z[i] = 0.f;
+        tmem_st_32x32(tmem + ((uint32_t)(warp * 32) << 16) + 448, z);
+        tmem_st_32x32(tmem + ((uint32_t)(warp * 32) << 16) + 480, z);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t bdesc = ((smem_u32(rsm2) >> 4) & 0x3fff) | (1u << 16);
+    const uint32_t idesc = umma_idesc_tf32(128, 32, false, false);
+    for (int nthr = 1; nthr <= 2; ++nthr) {
+        __syncthreads();
+        const long long t0 = clock64();
+        if ((tid & 31) == 0 && warp < nthr) {
+            for (int r = 0; r < reps; ++r) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_tf32_ts(tmem + (uint32_t)(warp * 64), tmem + 448 + 8 * kk, umma_desc_from(bdesc + 2 * kk), idesc, true);
+            }
+            umma_commit(&bar_done[warp]);
+        }
+        for (int w = 0; w < nthr; ++w) mbar_wait(&bar_done[w], (uint32_t)(nthr - 1 - (w == 1 ? 1 : 0)) & 1);
+        if (tid == 0) out[nthr - 1] = clock64() - t0;
+        __syncthreads();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+}  // namespace qrb200
+
+extern "C" int b200qr_probe_umma_rate2(long long *out2, int reps)
+{
+    if (!out2 || reps <= 0) return B200QR_EINVAL;
+    long long *d = nullptr;
+    if (cudaMalloc(&d, 2 * sizeof(long long)) != cudaSuccess) return B200QR_ECUDA;
+    cudaFuncSetAttribute(umma_rate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 33 * 1024);
+    umma_rate2_kernel<<<1, 128, 33 * 1024>>>(d, reps);
+    int rc = cudaDeviceSynchronize() == cudaSuccess ? B200QR_OK : B200QR_ECUDA;
+    if (rc == B200QR_OK) cudaMemcpy(out2, d, 2 * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return rc;
+}
+
 // out8: cycles for reps*4 MMAs: N = 32 (1 acc, 2 acc), 64 (1, 2), 128 (1, 2), 256 (1, -)
 extern "C" int b200qr_probe_umma_rate(long long *out8, int reps)
 {

@@ -81,6 +81,7 @@ int         b200qr_probe_panel(long long *cycles4, int reps);
  * hD2 <- A^T - W V^T when hW is given. */
 int         b200qr_probe_umma(const float *hA, const float *hV, const float *hW, float *hZ, float *hD2);
 int         b200qr_probe_umma_rate(long long *out8, int reps);   /* cycles of reps*4 tcgen05.mma (tf32, M=128, K=8): N=32,64,128,256 x {1,2} accumulators */
+int         b200qr_probe_umma_rate2(long long *out2, int reps);  /* one vs two issuing threads, reps*4 MMAs each (N = 32) */
 
 /* ---- plan: workspace + schedule for one (m, n) shape ----------------------------
  * Replaces the per-call cudaMalloc of task grid / queue / tau in cudaQRTask
