@@ -920,9 +920,13 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
             const int tcv = atoi(e);
             if (tcv != 0) pl->nc = (tcv == 2 || tcv == 3) && world == 1 && nvirt == 1 ? tcv + 2 : 3;
         } else if (world == 1 && nvirt == 1 && K >= 384) {
+            // take the workspace now: if it does not fit (or the allocation fails), the SIMT engine runs instead
             size_t free_b = 0, total_b = 0;
             const size_t wbytes = sizeof(float) * (size_t)m * K * TB * 6;
-            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > wbytes + ((size_t)1 << 30)) pl->nc = 5;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > wbytes + ((size_t)1 << 30)) {
+                if (cudaMalloc(&pl->d_W, wbytes) == cudaSuccess) pl->nc = 5;
+                else { pl->d_W = nullptr; (void)cudaGetLastError(); }
+            }
         }
     }
     if (pl->nc >= 4) {
@@ -973,7 +977,7 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
     CK(cudaMalloc(&pl->d_tauc, sizeof(float) * (size_t)K * p * TB));
     CK(cudaMemset(pl->d_tauc, 0, sizeof(float) * (size_t)K * p * TB));
     CK(cudaMemset(pl->d_prog, 0, sizeof(int) * (size_t)p * q));
-    if (pl->nc == 5) {
+    if (pl->nc == 5 && !pl->d_W) {
         const size_t wbytes = sizeof(float) * (size_t)m * K * TB * 6;
         if (cudaMalloc(&pl->d_W, wbytes) != cudaSuccess) return B200QR_ENOMEM;
     }
