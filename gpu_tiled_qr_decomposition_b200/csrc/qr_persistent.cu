@@ -67,6 +67,7 @@ struct Params {
     int la_enable;            // panel warps also update the next panel's column (look-ahead)
     const int *peer_prog[MAXW];     // progress words of every rank ([rank] = prog)
     const float *peer_tauc[MAXW];   // compact tau of every rank ([rank] = tauc)
+    int *prog_w[MAXW];              // tensor-core engine 3: every rank's progress words, writable (the builder warps push them)
     int npanel_ctas;          // > 0: role split -- CTAs [0, npanel_ctas) run only panel warps, the rest only sweeps;
                               // 0: every CTA runs both (small grids; NC = 1 only)
     int trace_mode;           // 1 = global sequence numbers, 2 = low 32 bits of %globaltimer (ns)
@@ -104,6 +105,7 @@ struct RankCtx {
     CUtensorMap mapW;               // tensor-core engine 3: workspace of pre-split operand tiles, box = the six tiles of one (i, k)
     CUtensorMap mapA4;              // tensor-core engine 3: this rank's matrix, box = one tile row of a sweep (4 tiles)
     CUtensorMap mapW2;              // tensor-core engine 3: the operand workspace, box = one operand (hi and lo tile)
+    CUtensorMap mapWp[MAXW];        // tensor-core engine 3: every rank's operand workspace ([rank] = own), box = the six tiles of one (i, k)
     int wcols;                      // (unused)
 };
 struct alignas(64) KernelArgs {
@@ -751,6 +753,7 @@ struct b200qr_plan_s {
     float *peer_A[MAXW];
     int *peer_prog[MAXW];
     float *peer_tauc[MAXW];
+    float *peer_W[MAXW];
     int *d_panel_tab = nullptr;
     long tile_tasks;
     int trace;
@@ -918,8 +921,8 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
         const char *e = getenv("QRB200_TC");
         if (e && *e) {
             const int tcv = atoi(e);
-            if (tcv != 0) pl->nc = (tcv == 2 || tcv == 3) && world == 1 && nvirt == 1 ? tcv + 2 : 3;
-        } else if (world == 1 && nvirt == 1 && K >= 384) {
+            if (tcv != 0) pl->nc = (tcv == 3 && nvirt == 1) || (tcv == 2 && world == 1 && nvirt == 1) ? tcv + 2 : 3;
+        } else if (nvirt == 1 && K >= 384 && (world == 1 || q >= 32 * world)) {
             // take the workspace now: if it does not fit (or the allocation fails), the SIMT engine runs instead
             size_t free_b = 0, total_b = 0;
             const size_t wbytes = sizeof(float) * (size_t)m * K * TB * 6;
@@ -951,10 +954,20 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
     std::vector<int> tab(2 * (size_t)(ns > 0 ? ns : 1)), ptab((size_t)(npan > 0 ? npan : 1));
     b200qr_sched_rank_tickets_skew(p, q, G, skew, rank, world, tab.data(), ns, ptab.data(), npan, &npan);
     // engine 3 on one GPU: lagged order (sweeps that run together share the step, so its operand tiles stay in L2)
-    if (pl->nc == 5 && world == 1 && !getenv("QRB200_SKEW")) {
+    if (pl->nc == 5 && !getenv("QRB200_SKEW")) {
         int lag = 16;
         if (const char *e = getenv("QRB200_LAG")) { int v = atoi(e); if (v >= 0) lag = v; }
-        if (b200qr_sched_sweep_order_lag(p, q, G, lag, tab.data(), ns) != ns) return B200QR_EINVAL;
+        const long total = b200qr_sched_sweep_order_lag(p, q, G, lag, nullptr, 0);
+        std::vector<int> all(2 * (size_t)(total > 0 ? total : 1));
+        b200qr_sched_sweep_order_lag(p, q, G, lag, all.data(), total);
+        long n = 0;
+        for (long t = 0; t < total; ++t)
+            if (all[2 * t + 1] % world == rank) {               // this rank's groups, in the global lagged order
+                if (n >= ns) return B200QR_EINVAL;
+                tab[2 * n] = all[2 * t]; tab[2 * n + 1] = all[2 * t + 1];
+                ++n;
+            }
+        if (n != ns) return B200QR_EINVAL;
     }
     ptab.resize((size_t)npan);
     pl->nsweeps = (int)ns;
@@ -986,8 +999,8 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
         CK(cudaMalloc(&pl->d_trace_off, sizeof(long long) * K));
         CK(cudaMemcpy(pl->d_trace_off, pl->trace_off.data(), sizeof(long long) * K, cudaMemcpyHostToDevice));
     }
-    for (int r = 0; r < MAXW; ++r) { pl->peer_A[r] = nullptr; pl->peer_prog[r] = nullptr; pl->peer_tauc[r] = nullptr; }
-    pl->peer_prog[rank] = pl->d_prog; pl->peer_tauc[rank] = pl->d_tauc;
+    for (int r = 0; r < MAXW; ++r) { pl->peer_A[r] = nullptr; pl->peer_prog[r] = nullptr; pl->peer_tauc[r] = nullptr; pl->peer_W[r] = nullptr; }
+    pl->peer_prog[rank] = pl->d_prog; pl->peer_tauc[rank] = pl->d_tauc; pl->peer_W[rank] = pl->d_W;
     return B200QR_OK;
 }
 
@@ -1011,7 +1024,7 @@ static int fill_rank_ctx(RankCtx *rc, b200qr_plan_s *pl, float *dA, int ldm)
     P.trace = (pl->trace && pl->trace != 3) ? pl->d_trace : nullptr; P.trace_off = pl->d_trace_off; P.trace_mode = pl->trace;
     if (getenv("QRB200_ONE_ENGINE")) P.trace_mode = 7;
     P.watchdog_ns = pl->watchdog_ns;
-    for (int r = 0; r < pl->world; ++r) { P.peer_prog[r] = pl->peer_prog[r]; P.peer_tauc[r] = pl->peer_tauc[r]; }
+    for (int r = 0; r < pl->world; ++r) { P.peer_prog[r] = pl->peer_prog[r]; P.peer_tauc[r] = pl->peer_tauc[r]; P.prog_w[r] = pl->peer_prog[r]; }
     int rc_ = make_tile_map(&rc->mapA, dA, pl->m, pl->n, ldm, true);
     for (int r = 0; r < pl->world && rc_ == B200QR_OK; ++r) {
         float *src = r == pl->rank ? dA : pl->peer_A[r];
@@ -1023,6 +1036,10 @@ static int fill_rank_ctx(RankCtx *rc, b200qr_plan_s *pl, float *dA, int ldm)
         rc_ = make_tile_map(&rc->mapW, pl->d_W, pl->m, 6 * pl->K * TB, pl->m, true, 6 * TB);
         if (rc_ == B200QR_OK) rc_ = make_tile_map(&rc->mapA4, dA, pl->m, pl->n, ldm, true, 4 * TB);
         if (rc_ == B200QR_OK) rc_ = make_tile_map(&rc->mapW2, pl->d_W, pl->m, 6 * pl->K * TB, pl->m, true, 2 * TB);
+        for (int r = 0; r < pl->world && rc_ == B200QR_OK; ++r) {
+            if (!pl->peer_W[r]) return B200QR_EINVAL;                // peers not connected
+            rc_ = make_tile_map(&rc->mapWp[r], pl->peer_W[r], pl->m, 6 * pl->K * TB, pl->m, true, 6 * TB);
+        }
         rc->wcols = 0;
     }
     return rc_;
@@ -1090,11 +1107,11 @@ int b200qr_factor_device(b200qr_plan_t pl, float *dA, int ldm, void *stream_)
 struct b200qr_dist_s {
     b200qr_plan_s plan;
     float *dA = nullptr;            // this rank's m x n matrix (ld = m); only the owned tile columns are used
-    void *opened[3 * MAXW] = {};    // IPC mappings to close
+    void *opened[4 * MAXW] = {};    // IPC mappings to close
     int connected = 0;
 };
 
-struct ipc_blob { cudaIpcMemHandle_t a, prog, tauc; };
+struct ipc_blob { cudaIpcMemHandle_t a, prog, tauc, w; int has_w; };
 
 int b200qr_dist_handle_bytes(void) { return (int)sizeof(ipc_blob); }
 
@@ -1140,6 +1157,9 @@ int b200qr_dist_export(b200qr_dist_t d, void *out_bytes)
     CK(cudaIpcGetMemHandle(&b.a, d->dA));
     CK(cudaIpcGetMemHandle(&b.prog, d->plan.d_prog));
     CK(cudaIpcGetMemHandle(&b.tauc, d->plan.d_tauc));
+    memset(&b.w, 0, sizeof b.w);
+    b.has_w = d->plan.d_W != nullptr;
+    if (b.has_w) CK(cudaIpcGetMemHandle(&b.w, d->plan.d_W));
     memcpy(out_bytes, &b, sizeof b);
     return B200QR_OK;
 }
@@ -1155,8 +1175,15 @@ int b200qr_dist_connect(b200qr_dist_t d, const void *all_bytes)
         CK(cudaIpcOpenMemHandle(&a, blobs[r].a, cudaIpcMemLazyEnablePeerAccess));
         CK(cudaIpcOpenMemHandle(&pr, blobs[r].prog, cudaIpcMemLazyEnablePeerAccess));
         CK(cudaIpcOpenMemHandle(&tc, blobs[r].tauc, cudaIpcMemLazyEnablePeerAccess));
-        d->opened[3 * r] = a; d->opened[3 * r + 1] = pr; d->opened[3 * r + 2] = tc;
+        d->opened[4 * r] = a; d->opened[4 * r + 1] = pr; d->opened[4 * r + 2] = tc;
         pl.peer_A[r] = (float *)a; pl.peer_prog[r] = (int *)pr; pl.peer_tauc[r] = (float *)tc;
+        if (pl.nc == 5) {                                             // every rank must have made the same choice
+            if (!blobs[r].has_w) return B200QR_EINVAL;
+            void *w = nullptr;
+            CK(cudaIpcOpenMemHandle(&w, blobs[r].w, cudaIpcMemLazyEnablePeerAccess));
+            d->opened[4 * r + 3] = w;
+            pl.peer_W[r] = (float *)w;
+        }
     }
     d->connected = 1;
     return B200QR_OK;
@@ -1173,6 +1200,7 @@ int b200qr_dist_connect_local(b200qr_dist_t *all, int world)
             all[r]->plan.peer_A[o] = all[o]->dA;
             all[r]->plan.peer_prog[o] = all[o]->plan.d_prog;
             all[r]->plan.peer_tauc[o] = all[o]->plan.d_tauc;
+            all[r]->plan.peer_W[o] = all[o]->plan.d_W;
         }
         all[r]->connected = 1;
     }
