@@ -418,17 +418,19 @@ def run_b200_multi(args, rank, world, local_rank):
     fp32 = C.c_double(0)
     q.check(L.b200qr_measure_fp32_peak(C.byref(fp32), 20000))
     achieved_tf = value * 1e-3
-    roofline = {"bound": "fp32-simt", "achieved": achieved_tf, "peak": fp32.value * 1e-3 * world, "unit": "TFLOP/s",
-                "frac": achieved_tf / (fp32.value * 1e-3 * world), "traffic": None,
-                "kernel": "tiledqr_persistent (one launch per rank per step)",
-                "peak_source": "FFMA microbench on rank 0 x %d GPUs; %s carries only HBM and bf16-tensor peaks"
-                               % (world, peak_src)}
+    variant = rk.variant
+    wpeaks = {k2: (v * world if isinstance(v, (int, float)) else v) for k2, v in peaks.items()}
+    roofline = roofline_of(variant, achieved_tf, fp32.value * 1e-3 * world, wpeaks, peak_src + " x %d GPUs" % world, n, ms_step)
+    roofline["kernel"] += " -- one launch per rank per step"
+    how = ("operand tiles (T factor, reflector block and its transpose, split for 3xTF32) broadcast by the panel owner's TMA "
+           "stores into every rank's workspace over NVLink, from inside the persistent kernel" if variant == 5 else
+           "reflector tiles read from the owner over NVLink inside the persistent kernel")
     line = {"metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic uniform[-1,1), torch cuda generator seed 5",
             "config": {"workload": "%dx%d square tiled QR, tile size 32, flat-tree TS kernels" % (n, n),
-                       "parallelism": "1-D block-cyclic tile columns (blocks of %d tile columns) over %d GPUs; reflector "
-                                      "tiles read from the owner over NVLink inside the persistent kernel" % (rk.block, world),
+                       "parallelism": "1-D block-cyclic tile columns (blocks of %d tile columns) over %d GPUs; %s"
+                                      % (rk.block, world, how), "kernel_variant": variant,
                        "l2": "input restored from a pristine copy before every timed step",
                        "persistent_grid_ctas_per_rank": rk.grid,
                        "single_gpu_same_workload_gflops": single},

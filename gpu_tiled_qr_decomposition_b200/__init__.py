@@ -28,7 +28,7 @@ EXPORTS = (
     "b200qr_sched_rank_tickets_skew", "b200qr_sched_sweep_order_lag",
     "b200qr_dist_create", "b200qr_dist_destroy", "b200qr_dist_handle_bytes", "b200qr_dist_export",
     "b200qr_dist_connect", "b200qr_dist_matrix", "b200qr_dist_tau_device", "b200qr_dist_block",
-    "b200qr_dist_owner", "b200qr_dist_grid", "b200qr_dist_read_trace", "b200qr_dist_tile_tasks", "b200qr_dist_reset", "b200qr_dist_factor",
+    "b200qr_dist_owner", "b200qr_dist_grid", "b200qr_dist_variant", "b200qr_dist_read_trace", "b200qr_dist_tile_tasks", "b200qr_dist_reset", "b200qr_dist_factor",
     "b200qr_dist_connect_local", "b200qr_dist_factor_group",
     "b200qr_batched_workspace_floats", "b200qr_batched_factor", "b200qr_batched_last_cuda_error",
     "b200qr_tsqr_create", "b200qr_tsqr_destroy", "b200qr_tsqr_levels", "b200qr_tsqr_factor",
@@ -290,6 +290,10 @@ class DistRank:
     @property
     def grid(self):
         return lib().b200qr_dist_grid(self._h)
+
+    @property
+    def variant(self):
+        return lib().b200qr_dist_variant(self._h)
 
     def owner(self, tile_col):
         return (tile_col // self.block) % self.world

@@ -1144,6 +1144,7 @@ float *b200qr_dist_matrix(b200qr_dist_t d) { return d ? d->dA : nullptr; }
 int b200qr_dist_block(b200qr_dist_t d) { return d ? d->plan.G : B200QR_EINVAL; }
 int b200qr_dist_owner(b200qr_dist_t d, int tile_col) { return d ? (tile_col / d->plan.G) % d->plan.world : B200QR_EINVAL; }
 int b200qr_dist_grid(b200qr_dist_t d) { return d ? d->plan.grid : B200QR_EINVAL; }
+int b200qr_dist_variant(b200qr_dist_t d) { return d ? d->plan.nc : B200QR_EINVAL; }
 const float *b200qr_dist_tau_device(b200qr_dist_t d) { return d ? d->plan.d_tauc : nullptr; }
 
 int b200qr_plan_read_trace(b200qr_plan_t pl, int *out6, long cap);

@@ -137,6 +137,7 @@ const float *b200qr_dist_tau_device(b200qr_dist_t d);        /* compact tau [(k*
 int    b200qr_dist_block(b200qr_dist_t d);                   /* tile columns per distribution block */
 int    b200qr_dist_owner(b200qr_dist_t d, int tile_col);     /* rank that owns a tile column */
 int    b200qr_dist_grid(b200qr_dist_t d);
+int  b200qr_dist_variant(b200qr_dist_t d);             /* kernel variant of this rank's plan (2: SIMT sweeps, 5: tensor-core engine) */
 int    b200qr_dist_read_trace(b200qr_dist_t d, int *out6, long cap);   /* opts.trace; tasks of other ranks read -1 */
 long   b200qr_dist_tile_tasks(b200qr_dist_t d);
 int    b200qr_dist_reset(b200qr_dist_t d, void *stream);

@@ -56,3 +56,23 @@ def test_two_ranks_on_one_device_match_single_gpu(cuda, qr, po, m, n):
     assert np.max(np.abs(out - ref_out)) <= 1e-4 * max(1.0, scale)
     for rk in ranks:
         rk.close()
+
+
+def test_tensor_core_engine_on_two_real_gpus(cuda):
+    """The multi-GPU form of the tensor-core engine (operand tiles broadcast by TMA stores into every rank's workspace)
+    must give the single-GPU engine's result bit for bit.  Needs two visible GPUs (skipped on a one-GPU box)."""
+    import os
+    import subprocess
+    import sys
+    torch = cuda
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, QRB200_WATCHDOG_MS="30000")
+    env.pop("QRB200_TC", None)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533",
+                        os.path.join(root, "tools", "dist_tc3_check.py"), "12288"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "single-GPU variant 5" in r.stdout and "identical: True" in r.stdout, r.stdout[-2000:]
