@@ -942,6 +942,7 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
     pl->G = G;
     pl->la_enable = 0;
     if (const char *e = getenv("QRB200_LOOKAHEAD")) pl->la_enable = atoi(e) != 0 && pl->nc != 5;
+    if (pl->nc == 5 && getenv("QRB200_SYSFENCE")) pl->la_enable = 2;      // engine 3 has no look-ahead: the field carries this experiment flag
 
     // this rank's tickets: sweeps of its blocks in the global skewed order, panels of its tile columns
     // skew of the sweep order: a tensor-core sweep row is several times faster than a TSQRT of the panel
@@ -955,7 +956,10 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
     b200qr_sched_rank_tickets_skew(p, q, G, skew, rank, world, tab.data(), ns, ptab.data(), npan, &npan);
     // engine 3 on one GPU: lagged order (sweeps that run together share the step, so its operand tiles stay in L2)
     if (pl->nc == 5 && !getenv("QRB200_SKEW")) {
-        int lag = 16;
+        // LAG: far sweeps of a step start this many steps behind its panel, which should have finished by then.  With
+        // W ranks the steps go by ~W times faster while a panel chain takes as long as ever (measured: one GPU 16, four
+        // GPUs 48 best of {16, 48, 128}).
+        int lag = 16 + 10 * (world - 1);
         if (const char *e = getenv("QRB200_LAG")) { int v = atoi(e); if (v >= 0) lag = v; }
         const long total = b200qr_sched_sweep_order_lag(p, q, G, lag, nullptr, 0);
         std::vector<int> all(2 * (size_t)(total > 0 ? total : 1));
