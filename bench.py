@@ -164,13 +164,20 @@ def gram_check(torch, d, A0, c0, c1):
     return (torch.linalg.norm(R.t() @ R - G2) / torch.linalg.norm(G2)).item()
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the `ncu --set full` captures summarised under profiles/
+# (r1_simt_8192_summary.txt, r1_tc3_16384_summary.txt), keyed by (kernel variant, n); other shapes report null.
+NCU_TRAFFIC_BYTES = {(2, 8192): 4.175e9 + 7.903e9, (5, 16384): 189.27e9 + 177.82e9}
+
+
 def roofline_of(variant, achieved_tf, fp32_peak_tf, peaks, peak_src, n, ms_step):
     """The factorisation is one persistent kernel, so the kernel's roofline is the step's.  Variants 1 / 2 apply the
     reflectors on the FP32 SIMT pipe (bound: the FFMA rate, measured in this process).  Variant 5 runs the trailing
     update as 3xTF32 tcgen05 products: the bound is the tensor pipe at a sixth of the measured dense bf16 rate (TF32
     runs at half the bf16 rate, three passes per product); the fraction of the FP32 SIMT peak -- the north-star's
     '% of B200 peak for the working precision' -- is reported next to it."""
-    common = {"achieved": achieved_tf, "unit": "TFLOP/s", "traffic": None,
+    common = {"achieved": achieved_tf, "unit": "TFLOP/s", "traffic": NCU_TRAFFIC_BYTES.get((variant, n)),
+              "traffic_note": "DRAM bytes per launch (ncu), vs 8*m*n = %.3g algorithmic: the right-looking sweeps stream the "
+                              "trailing tiles once per step; L2 absorbs what fits" % (8.0 * n * n),
               "frac_of_fp32_simt_peak": achieved_tf / fp32_peak_tf, "fp32_simt_peak": fp32_peak_tf,
               "frac_of_bf16_tensor_peak": achieved_tf / peaks["bf16_tflops"],
               "hbm_algorithmic_gbs": 8.0 * n * n / (ms_step * 1e-3) * 1e-9}
