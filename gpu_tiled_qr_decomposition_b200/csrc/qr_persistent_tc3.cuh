@@ -1,28 +1,28 @@
-// qr_persistent_tc3.cuh -- third tensor-core sweep engine (QRB200_TC=3), included by qr_persistent.cu.
+// qr_persistent_tc3.cuh -- third tensor-core sweep engine (QRB200_TC=3; the default for large matrices), included by
+// qr_persistent.cu.  Design, measurements and what bounds it: DESIGN.md section 6, profiles/r1_measurements.md.
 //
-// Same mathematics as the other two tensor-core engines -- the reference's TSMQR / UNMQR
-// (qrdecomp.c:620-644, 736-762) in compact-WY form, every product 3xTF32 on tcgen05 with fp32
-// accumulation in tensor memory -- rebuilt around what the first two measured: a tile row of a sweep
-// is a CHAIN through the resident tile row k (c_top), and the only way to make the chain short is to
-// take everything else off it.  For a block of 32 reflectors (V, T) and 128 matrix columns:
-//     Y = C_bot^T V                  off the chain, issued rows ahead                (issuer A)
-//     S = c_top + Y                  per thread                                        (chain warps)
-//     W = S T                        tcgen05.mma, K = 32                               (issuer B)
-//     c_top -= W                     per thread                                        (chain warps)
-//     C_bot^T -= W V^T               off the chain: accumulator preloaded with C_bot^T (issuer B)
-// so one chain step is: TMEM load, 32 adds, split, TMEM store, 12 small MMAs.  T is NOT rebuilt by
-// every sweep: the panel warp that factors a tile also emits its T factor and the transposed block V^T
-// (build_t_warp, qr_device.cuh) into two workspace matrices with the layout of A, and the sweeps
-// TMA-load them next to V.  Warp roles of a sweep CTA (13 warps, one CTA per SM):
-//     loader   polls the progress words, TMA-loads the row's 4 tiles into the C ring (8 stages) and
-//              V, T, V^T into the operand ring (4 stages)
-//     bulk x4  thread = matrix column: preloads the product-3 accumulator with the column and writes
-//              its hi / lo halves as the A operand of product 1 (all in tensor memory, 3 buffers);
-//              three rows later reads the finished column back into the C stage
+// Same mathematics as the other two tensor-core engines -- the reference's TSMQR / UNMQR (qrdecomp.c:620-644, 736-762)
+// in compact-WY form, every product 3xTF32 on tcgen05 with fp32 accumulation in tensor memory -- rebuilt around what
+// the first two measured: a tile row of a sweep is a CHAIN through the resident tile row k (c_top), and the only way to
+// make the chain short is to take everything else off it.  For a block of 32 reflectors (V, T) and 128 matrix columns:
+//     Y = C_bot^T V                  product 1: off the chain, issued rows ahead       (issuer A)
+//     S = c_top + Y                  per thread                                          (chain warps)
+//     W = S T                        product 2: the only MMA on the chain                (issuer B)
+//     c_top -= W                     per thread                                          (chain warps)
+//     C_bot^T -= W V^T               product 3: off the chain, accumulator preloaded     (issuer C)
+// T is NOT rebuilt by every sweep: a panel CTA runs pairs of warps -- the factor warp runs GEQRT / the TSQRT chain, its
+// builder warp forms T and the six operand tiles already split into 3xTF32 halves (build_t_warp, qr_device.cuh), stores
+// them into every rank's workspace and publishes the tile (factor_main / builder_main in the body file).
+// Warp roles of a sweep CTA (13 warps, one CTA per SM, each role a function with a register allocation of its own):
+//     loader   polls the progress words four rows ahead; one TMA box per tile row (IN ring) and per operand (V / T /
+//              V^T rings), every stream gated by its own ring
+//     bulk x4  thread = matrix column: preloads the product-3 accumulator with the column and writes its hi / lo halves
+//              as the A operand of product 1 (tensor memory); four rows later reads the finished column back into an
+//              OUT stage
 //     chain x4 thread = matrix column: the chain above; c_top stays in registers
-//     storer   TMA-stores finished rows (two stores in flight), publishes their progress words
-//     issuers A / B / C   one thread each issues the MMAs of product 1 / 2 / 3
-// Panel chains run in CTAs of their own (four panel warps each), as in engine 2.
+//     storer   TMA-stores finished rows, publishes their progress words two rows per fence
+//     issuers A / B / C   one thread each issues the MMAs of product 1 / 2 / 3 (a thread issues one tcgen05.mma of this
+//              size per ~50 cycles; the pipe takes several threads at once)
 #pragma once
 #include "qr_umma.cuh"
 
