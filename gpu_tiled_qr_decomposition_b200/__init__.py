@@ -9,7 +9,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libqrb200.so")
+LIB_PATH = os.environ.get("QRB200_LIB") or os.path.join(HERE, "libqrb200.so")   # QRB200_LIB: A/B runs of kernel variants
 
 TILE = 32
 QRS, SAPP, QRD, DAPP = 0, 1, 2, 3

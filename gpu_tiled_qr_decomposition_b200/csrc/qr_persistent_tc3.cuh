@@ -17,7 +17,7 @@
 //     loader   polls the progress words four rows ahead; one TMA box per tile row (IN ring) and per operand (V / T /
 //              V^T rings), every stream gated by its own ring
 //     bulk x4  thread = matrix column: preloads the product-3 accumulator with the column and writes its hi / lo halves
-//              as the A operand of product 1 (tensor memory); four rows later reads the finished column back into an
+//              as the A operand of product 1 (tensor memory); three rows later reads the finished column back into an
 //              OUT stage
 //     chain x4 thread = matrix column: the chain above; c_top stays in registers
 //     storer   TMA-stores finished rows, publishes their progress words two rows per fence
