@@ -273,7 +273,7 @@ def run_b200_single(args):
         L.cudaQRTask(C.c_void_p(h.data_ptr()), n, n, n, 128)
         e2e_s += time.perf_counter() - t0
     e2e_val = flops / (e2e_s / e2e_steps) * 1e-9
-    e2e_err = float((h[:64, :64] - d.cpu()[:64, :64]).abs().max())
+    e2e_err = float((h - d.cpu()).abs().max())                     # whole matrix, vs the device-resident path
 
     peaks, peak_src = measured_peaks()
     fp32 = C.c_double(0)
@@ -303,7 +303,8 @@ def run_b200_single(args):
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "GFLOP/s", "h2d_bytes_per_step": 4 * n * n,
                     "d2h_bytes_per_step": 4 * n * n, "api": "cudaQRTask(host float*, m, n, ldm, maxblocks) on pinned "
-                    "host memory (workspace cached between calls of one shape)", "steps": e2e_steps,
+                    "host memory (workspace cached between calls of one shape; copies overlapped with the kernel: tile "
+                    "columns stream in behind progress words, finished columns stream out)", "steps": e2e_steps,
                     "max_abs_diff_vs_device_path": e2e_err},
             "gpu_launches": args.steps * 1, "clocks": clocks, "check": {"gram_rel_err": gram}}
     if north is not None:

@@ -35,6 +35,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <unistd.h>
 
 namespace qrb200 {
 
@@ -349,7 +350,12 @@ __device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int p
         if (la) tma_store_2d(mapA, k * TB, (k + 1) * TB, pla0);
         bulk_commit();
         bulk_wait_all();
-        if (la) { __threadfence(); st_release(prog_la + k, k + 1); }
+        __threadfence();
+        if (la) st_release(prog_la + k, k + 1);
+        // "tile column k is final": the diagonal word moves on to k + 2 once the last store of the panel has landed
+        // (every reader of this word asks for >= k + 1).  The host uses it to copy finished columns back while the
+        // kernel is still running (cudaQRTask).
+        st_release(prog_col + k, k + 2);
     }
     __syncwarp();
 }
@@ -1049,9 +1055,12 @@ static int fill_rank_ctx(RankCtx *rc, b200qr_plan_s *pl, float *dA, int ldm)
     return rc_;
 }
 
-static int reset_progress(b200qr_plan_s *pl, cudaStream_t stream)
+// fill = 0: every tile has its input (the normal case); fill = 0xff: every word is -1 = "this tile's input has not
+// arrived yet" -- the step-0 tasks poll for >= 0 like any other dependency, and whoever brings the data in sets the
+// words of a tile column to 0 afterwards (the overlapped host path of cudaQRTask).
+static int reset_progress(b200qr_plan_s *pl, cudaStream_t stream, int fill = 0)
 {
-    CK(cudaMemsetAsync(pl->d_prog, 0, sizeof(int) * (size_t)pl->p * pl->q, stream));
+    CK(cudaMemsetAsync(pl->d_prog, fill, sizeof(int) * (size_t)pl->p * pl->q, stream));
     CK(cudaMemsetAsync(pl->d_ctr, 0, sizeof(int) * CTR_INTS, stream));
     if (pl->trace && pl->trace != 3) CK(cudaMemsetAsync(pl->d_trace, 0xff, sizeof(int) * 2 * (size_t)pl->tile_tasks, stream));
     return B200QR_OK;
@@ -1093,6 +1102,16 @@ int b200qr_plan_debug_counters(b200qr_plan_t pl, unsigned long long *out, int n)
 long b200qr_plan_tile_tasks(b200qr_plan_t pl) { return pl ? pl->tile_tasks : B200QR_EINVAL; }
 long b200qr_plan_macro_tasks(b200qr_plan_t pl) { return pl ? (long)pl->nsweeps + pl->npanels : B200QR_EINVAL; }
 const float *b200qr_plan_tau_device(b200qr_plan_t pl) { return pl ? pl->d_tauc : nullptr; }
+
+// the launch alone: the caller has reset the progress words and counters on `stream`
+static int factor_launch(b200qr_plan_t pl, float *dA, int ldm, cudaStream_t stream)
+{
+    KernelArgs ka;
+    ka.nvirt = 1;
+    int rc = fill_rank_ctx(&ka.rc[0], pl, dA, ldm);
+    if (rc != B200QR_OK) return rc;
+    return launch(&ka, pl->nc, pl->grid, stream);
+}
 
 int b200qr_factor_device(b200qr_plan_t pl, float *dA, int ldm, void *stream_)
 {
@@ -1340,6 +1359,10 @@ struct LegacyCache {
     float *dA = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     int m = 0, n = 0, grid_ctas = 0, dev = -1;
+    // overlapped host path: kernel / host-to-device / device-to-host / poll streams, "words reset" event, pinned scratch
+    cudaStream_t ks = nullptr, hs = nullptr, ds = nullptr, ps = nullptr;
+    cudaEvent_t evr = nullptr;
+    int *h_zero = nullptr, *h_prog = nullptr;
 };
 static LegacyCache g_cache;
 
@@ -1349,7 +1372,123 @@ void b200qr_release_cache(void)
     if (g_cache.dA) cudaFree(g_cache.dA);
     if (g_cache.e0) cudaEventDestroy(g_cache.e0);
     if (g_cache.e1) cudaEventDestroy(g_cache.e1);
+    if (g_cache.evr) cudaEventDestroy(g_cache.evr);
+    if (g_cache.ks) cudaStreamDestroy(g_cache.ks);
+    if (g_cache.hs) cudaStreamDestroy(g_cache.hs);
+    if (g_cache.ds) cudaStreamDestroy(g_cache.ds);
+    if (g_cache.ps) cudaStreamDestroy(g_cache.ps);
+    if (g_cache.h_zero) cudaFreeHost(g_cache.h_zero);
+    if (g_cache.h_prog) cudaFreeHost(g_cache.h_prog);
     g_cache = LegacyCache();
+}
+
+// ---- cudaQRTask with the copies overlapped (pinned host matrices of >= 32 MB; QRB200_OVERLAP=1 / 0 forces / forbids)
+// The reference copies the matrix in, runs its kernel, copies it out (gpucalc.cu:1614-1670).  Here the three overlap:
+//   in   the progress words start at -1 ("input not here yet") instead of 0; the matrix travels in chunks of tile
+//        columns on a copy stream, each followed by a copy of zeros onto the chunk's words.  The persistent kernel is
+//        already running: its step-0 tasks wait for their tile's word like for any other dependency, and the ticket
+//        order hands the far tile columns out last anyway;
+//   out  tile column j is final once its words read {i + 1 above the diagonal, j + 2 on it, j + 1 below}; the host polls
+//        the words and copies finished columns back while the kernel works on the rest.
+// Everything that touches the device while the kernel runs is a copy-engine transfer: the kernel holds every SM's
+// registers, so a memset or any other kernel queued behind it would never start.
+constexpr int OVL_WINDOW = 128;      // tile columns of progress words fetched per poll
+constexpr int OVL_MAXCHUNK = 16;     // tile columns per transfer, at most
+
+static bool host_pinned(const void *ptr)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+static bool column_final(const int *w, int j, int p, int K)
+{
+    for (int i = 0; i < p; ++i) {
+        const int lo = i < j ? i : j;
+        const int want = (i == j && j < K) ? j + 2 : (lo + 1 < K ? lo + 1 : K);
+        if (w[i] != want) return false;
+    }
+    return true;
+}
+
+// returns 0 when done (result in mat), 1 when the overlapped path is not available (nothing touched), -1 on errors
+static int legacy_overlapped(float *mat, int m, int n, int ldm, bool quiet)
+{
+    LegacyCache &c = g_cache;
+    b200qr_plan_s *pl = c.plan;
+    const int p = pl->p, q = pl->q, K = pl->K;
+    if (!c.ks) {
+        bool ok = cudaStreamCreateWithFlags(&c.ks, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&c.hs, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&c.ds, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&c.ps, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&c.evr, cudaEventDisableTiming) == cudaSuccess &&
+                  cudaMallocHost(&c.h_zero, sizeof(int) * (size_t)OVL_MAXCHUNK * p) == cudaSuccess &&
+                  cudaMallocHost(&c.h_prog, sizeof(int) * (size_t)OVL_WINDOW * p) == cudaSuccess;
+        if (!ok) { (void)cudaGetLastError(); return 1; }
+        memset(c.h_zero, 0, sizeof(int) * (size_t)OVL_MAXCHUNK * p);
+    }
+    long long ctl = (8ll << 20) / ((long long)m * TB * (long long)sizeof(float));
+    const int ct = ctl < 1 ? 1 : (ctl > OVL_MAXCHUNK ? OVL_MAXCHUNK : (int)ctl);
+    float *dA = c.dA;
+    bool bad = false;
+    auto ck = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess && !bad) { bad = true; g_last_cuda = (int)e; printf("error %s: %s\n", what, cudaGetErrorString(e)); }
+    };
+    if (reset_progress(pl, c.ks, 0xff) != B200QR_OK) { printf("error resetting the progress words\n"); return -1; }
+    ck(cudaEventRecord(c.evr, c.ks), "recording");
+    ck(cudaEventRecord(c.e0, c.ks), "recording");
+    int rc = factor_launch(pl, dA, m, c.ks);
+    ck(cudaEventRecord(c.e1, c.ks), "recording");
+    if (rc != B200QR_OK) { printf("error running QR kernel: %s\n", b200qr_strerror(rc)); cudaStreamSynchronize(c.ks); return -1; }
+    // ---- in: chunks of tile columns, each followed by zeros onto its progress words
+    ck(cudaStreamWaitEvent(c.hs, c.evr, 0), "ordering the copy stream");
+    for (int j0 = 0; j0 < q; j0 += ct) {
+        const int nt = q - j0 < ct ? q - j0 : ct;
+        ck(cudaMemcpy2DAsync(dA + (size_t)j0 * TB * m, sizeof(float) * m, mat + (size_t)j0 * TB * ldm, sizeof(float) * ldm,
+                             sizeof(float) * m, (size_t)nt * TB, cudaMemcpyHostToDevice, c.hs), "cpying dev mat");
+        ck(cudaMemcpyAsync(pl->d_prog + (size_t)j0 * p, c.h_zero, sizeof(int) * (size_t)nt * p, cudaMemcpyHostToDevice, c.hs),
+           "releasing tile columns");
+    }
+    if (bad) {
+        // the kernel may be waiting for columns that will never arrive: release everything, then collect it
+        for (int j0 = 0; j0 < q; j0 += OVL_MAXCHUNK)
+            cudaMemcpyAsync(pl->d_prog + (size_t)j0 * p, c.h_zero, sizeof(int) * (size_t)(q - j0 < OVL_MAXCHUNK ? q - j0 : OVL_MAXCHUNK) * p,
+                            cudaMemcpyHostToDevice, c.hs);
+        cudaDeviceSynchronize();
+        return -1;
+    }
+    // ---- out: finished tile columns, while the kernel runs
+    auto copy_back = [&](int j0, int j1) {
+        ck(cudaMemcpy2DAsync(mat + (size_t)j0 * TB * ldm, sizeof(float) * ldm, dA + (size_t)j0 * TB * m, sizeof(float) * m,
+                             sizeof(float) * m, (size_t)(j1 - j0) * TB, cudaMemcpyDeviceToHost, c.ds), "copy back");
+    };
+    int jdone = 0, jready = 0;
+    while (jdone < q && !bad) {
+        if (cudaEventQuery(c.e1) != cudaErrorNotReady) break;          // finished (or failed): the rest goes in one piece
+        const int w = q - jready < OVL_WINDOW ? q - jready : OVL_WINDOW;
+        if (w > 0) {
+            ck(cudaMemcpyAsync(c.h_prog, pl->d_prog + (size_t)jready * p, sizeof(int) * (size_t)w * p, cudaMemcpyDeviceToHost, c.ps),
+               "polling");
+            ck(cudaStreamSynchronize(c.ps), "polling");
+            int adv = 0;
+            while (adv < w && column_final(c.h_prog + (size_t)adv * p, jready + adv, p, K)) ++adv;
+            jready += adv;
+        }
+        if (jready - jdone >= ct || (jready == q && jready > jdone)) { copy_back(jdone, jready); jdone = jready; }
+        else usleep(50);
+    }
+    (void)cudaGetLastError();                                          // cudaErrorNotReady of the queries
+    cudaError_t se = cudaEventSynchronize(c.e1);
+    if (se != cudaSuccess) { printf("error running QR kernel: %s (%d)\n", cudaGetErrorString(se), (int)se); g_last_cuda = (int)se; bad = true; }
+    if (!bad && jdone < q) copy_back(jdone, q);
+    cudaStreamSynchronize(c.hs);
+    cudaStreamSynchronize(c.ds);
+    float ms = 0.f;
+    if (!bad) cudaEventElapsedTime(&ms, c.e0, c.e1);
+    if (!quiet) printf("GPU: %5.3f ms\n", ms);                         // gpucalc.cu:1647 (here it includes waiting for the input)
+    return bad ? -1 : 0;
 }
 
 static bool env_on(const char *name)
@@ -1393,6 +1532,19 @@ void cudaQRTask(float *mat, int m, int n, int ldm, int maxblocks)
         g_cache.m = m; g_cache.n = n; g_cache.grid_ctas = opts.grid_ctas; g_cache.dev = dev;
     }
     float *dA = g_cache.dA;
+    {
+        const char *ov = getenv("QRB200_OVERLAP");
+        const int nc = g_cache.plan->nc;
+        const bool able = nc == 1 || nc == 2 || nc == 5;               // engines that publish "tile column final"
+        const bool want = ov && *ov ? atoi(ov) != 0 : (sizeof(float) * (size_t)m * n >= ((size_t)32 << 20) && host_pinned(mat));
+        if (able && want) {
+            const int orc = legacy_overlapped(mat, m, n, ldm, quiet);
+            if (orc <= 0) {
+                if (env_on("QRB200_COMPAT_RESET")) { b200qr_release_cache(); cudaDeviceReset(); }
+                return;
+            }
+        }
+    }
     if (cudaMemcpy2D(dA, sizeof(float) * m, mat, sizeof(float) * ldm, sizeof(float) * m, n,
                      cudaMemcpyHostToDevice) != cudaSuccess)
         printf("error cpying dev mat\n");
