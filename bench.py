@@ -134,9 +134,10 @@ def run_reference(args, rank, world):
     sample = "%dx%d RANDZO matrix, b=32, taskQRP_threads with %d pthreads, -O3 -march=x86-64-v3" % (n, n, cores)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%dx%d square tiled QR, b=32 (bounded sample of the 8192x8192 workload: the "
-                                   "reference's O(p*q)-scan scheduler needs minutes at 8192)" % (n, n)},
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%dx%d square tiled QR, b=32 (bounded sample of the %s workload of the b200 arm: the "
+                                   "reference's O(p*q)-scan scheduler needs minutes at 8192 and has no multi-GPU path)"
+                                   % (n, n, "8192x8192" if args.gpus <= 1 else "%dx%d" % (args.multi_size, args.multi_size))},
             "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "host_cpus": os.cpu_count()}

@@ -31,7 +31,7 @@ EXPORTS = (
     "b200qr_dist_owner", "b200qr_dist_grid", "b200qr_dist_variant", "b200qr_dist_read_trace", "b200qr_dist_tile_tasks", "b200qr_dist_reset", "b200qr_dist_factor",
     "b200qr_dist_connect_local", "b200qr_dist_factor_group",
     "b200qr_batched_workspace_floats", "b200qr_batched_factor", "b200qr_batched_last_cuda_error",
-    "b200qr_tsqr_create", "b200qr_tsqr_destroy", "b200qr_tsqr_levels", "b200qr_tsqr_factor",
+    "b200qr_tsqr_create", "b200qr_tsqr_create_streaming", "b200qr_tsqr_destroy", "b200qr_tsqr_levels", "b200qr_tsqr_factor",
     "b200qr_apply_q", "b200qr_release_cache", "cudaQRTask", "cudaQRFull", "testDAPP", "doCUDADAPP",
 )
 
@@ -134,6 +134,7 @@ def lib():
         L.b200qr_batched_workspace_floats.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
         L.b200qr_batched_factor.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int, vp, vp, vp]
         L.b200qr_tsqr_create.argtypes = [C.POINTER(vp), C.c_longlong, C.c_int, C.c_int, C.c_int]
+        L.b200qr_tsqr_create_streaming.argtypes = [C.POINTER(vp), C.c_longlong, C.c_int, C.c_int]
         L.b200qr_tsqr_destroy.argtypes = [vp]
         L.b200qr_tsqr_levels.argtypes = [vp]
         L.b200qr_tsqr_factor.argtypes = [vp, vp, C.c_longlong, vp, vp]

@@ -81,3 +81,34 @@ def test_tsqr_r_factor(cuda, qr, m, n, leaf, fanin):
     R64 = torch.linalg.qr(Ad, mode="r").R
     s = torch.sign(torch.diagonal(R64)) * torch.sign(torch.diagonal(Rm))
     assert (torch.max(torch.abs(Rm - s[:, None] * R64)) / torch.max(torch.abs(R64))).item() <= 1e-4
+
+
+@pytest.mark.parametrize("m,n,strips", [(4096, 256, 0), (8192, 128, 3), (12288, 256, 5), (2048, 64, 1), (5120, 256, 0),
+                                          (262144, 256, 0), (4128, 32, 2)])
+def test_tsqr_streaming_r_factor(cuda, qr, m, n, strips):
+    """Streaming TSQR engine (strips of rows, R resident in shared memory, tree over the strips' R factors):
+    same contract as the leaf-batch tree -- R upper triangular, R^T R = A^T A, R = LAPACK's up to row signs."""
+    torch = cuda
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = torch.rand((n, m), generator=g, device="cuda", dtype=torch.float32) * 2 - 1    # column-major m x n
+    d = A.clone()
+    h = C.c_void_p()
+    qr.check(qr.lib().b200qr_tsqr_create_streaming(C.byref(h), m, n, strips))
+    R = torch.full((n, n), 7.0, dtype=torch.float32, device="cuda")
+    for _ in range(2):                                   # a plan is reusable
+        d.copy_(A)
+        qr.check(qr.lib().b200qr_tsqr_factor(h, C.c_void_p(d.data_ptr()), m, C.c_void_p(R.data_ptr()),
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert qr.lib().b200qr_tsqr_levels(h) >= 1
+    qr.lib().b200qr_tsqr_destroy(h)
+    Rm = R.t().double()
+    assert torch.count_nonzero(torch.tril(Rm, -1)) == 0
+    Ad = A.t().double()
+    G = Ad.t() @ Ad
+    assert (torch.linalg.norm(Rm.t() @ Rm - G) / torch.linalg.norm(G)).item() <= 50 * float(np.finfo(np.float32).eps)
+    R64 = torch.linalg.qr(Ad, mode="r").R
+    s = torch.sign(torch.diagonal(R64)) * torch.sign(torch.diagonal(Rm))
+    assert (torch.max(torch.abs(Rm - s[:, None] * R64)) / torch.max(torch.abs(R64))).item() <= 1e-4
+    # the reflectors left in place are bounded (|v| <= 1 elementwise for a Householder vector scaled by its pivot)
+    assert torch.isfinite(d).all() and d.abs().max().item() <= 1.0 + 1e-6

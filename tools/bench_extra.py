@@ -69,6 +69,27 @@ def tsqr(m=4194304, n=256, leaf=2048, fanin=4):
     L.b200qr_tsqr_destroy(h)
 
 
+def tsqr_streaming(m=4194304, n=256, strips=0):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A0 = torch.rand((n, m), generator=g, device="cuda") * 2 - 1
+    d = torch.empty_like(A0)
+    h = C.c_void_p()
+    q.check(L.b200qr_tsqr_create_streaming(C.byref(h), m, n, strips))
+    R = torch.zeros((n, n), device="cuda")
+    fn = lambda: q.check(L.b200qr_tsqr_factor(h, C.c_void_p(d.data_ptr()), m, C.c_void_p(R.data_ptr()), C.c_void_p(stream)))
+    ms = timeit(fn, lambda: d.copy_(A0))
+    flops = 2.0 * m * n * n - 2.0 * n ** 3 / 3
+    Rm = R.t().double()
+    G = torch.zeros((n, n), dtype=torch.float64, device="cuda")
+    for c in range(0, m, 1 << 20):
+        blk = A0[:, c:c + (1 << 20)].double()
+        G += blk @ blk.t()
+    err = (torch.linalg.norm(Rm.t() @ Rm - G) / torch.linalg.norm(G)).item()
+    print(json.dumps({"workload": "TSQR %dx%d, streaming engine, %d strips, %d levels" % (m, n, strips, L.b200qr_tsqr_levels(h)),
+                      "ms": ms, "gflops": flops / ms * 1e-6, "hbm_algorithmic_gbs": 8.0 * m * n / ms * 1e-6, "gram_rel_err": err}))
+    L.b200qr_tsqr_destroy(h)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("all", "batched"):
@@ -76,3 +97,6 @@ if __name__ == "__main__":
     if which in ("all", "tsqr"):
         for leaf in (512, 2048):
             tsqr(leaf=leaf)
+    if which in ("all", "tsqr", "stream"):
+        for strips in (0, 296, 592):
+            tsqr_streaming(strips=strips)
