@@ -333,6 +333,96 @@ class DistRank:
             self._h = C.c_void_p()
 
 
+class Tsqr:
+    """Tall-skinny QR of an m x n matrix, n <= 256 (b200qr_tsqr_*).  Default: the streaming engine (strips of rows, the
+    n x n triangle resident in shared memory); leaf_rows > 0 selects the leaf-batch tree (reference tile layout per leaf)."""
+
+    def __init__(self, m, n, strips=0, leaf_rows=0, fanin=4):
+        self.m, self.n = m, n
+        self._h = C.c_void_p()
+        if leaf_rows:
+            check(lib().b200qr_tsqr_create(C.byref(self._h), m, n, leaf_rows, fanin), "b200qr_tsqr_create")
+        else:
+            check(lib().b200qr_tsqr_create_streaming(C.byref(self._h), m, n, strips), "b200qr_tsqr_create_streaming")
+
+    @property
+    def levels(self):
+        return lib().b200qr_tsqr_levels(self._h)
+
+    def factor(self, dA_ptr, ldm, dR_ptr, stream=0):
+        """dA (m x n, column-major, ldm) is overwritten with the leaf reflectors, dR (n x n, ld = n) receives R."""
+        check(lib().b200qr_tsqr_factor(self._h, C.c_void_p(dA_ptr), ldm, C.c_void_p(dR_ptr), C.c_void_p(stream)),
+              "b200qr_tsqr_factor")
+
+    def close(self):
+        if self._h:
+            lib().b200qr_tsqr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def tsqr_gather_stack(R_local, world, group=None):
+    """The exchange step of the multi-GPU TSQR: all-gather the ranks' n x n R factors (column-major: a torch (n, n)
+    tensor indexed [column, row]) and lay them out as the column-major (world*n) x n stack the top-level reduction reads,
+    element (g*n + r, c) at [c, g*n + r].  NCCL over NVLink on GPUs; gloo in the CPU tests."""
+    import torch
+    import torch.distributed as dist
+    n = R_local.shape[0]
+    parts = [torch.empty_like(R_local) for _ in range(world)]
+    dist.all_gather(parts, R_local.contiguous(), group=group)
+    return torch.stack(parts, 0).permute(1, 0, 2).reshape(n, world * n).contiguous()
+
+
+class TsqrDist:
+    """BASELINE.json configs[3] on W GPUs: the rows are split into W contiguous blocks, rank r owns block r.
+    Every rank reduces its block to an n x n R factor (streaming engine), the factors are all-gathered -- the path's one
+    real exchange step, W x 256 KB at n = 256 -- and every rank reduces the stack of W factors redundantly, so all ranks
+    end with the same R.  The implicit Q is the rank's leaf reflectors (in place in its block) plus the two trees.
+    `local_reduce(A, R)` / `top_reduce(stack, R)` default to the CUDA plans; the gloo CPU test injects the oracle to
+    exercise the exchange without a GPU."""
+
+    def __init__(self, m_local, n, world, group=None, local_reduce=None, top_reduce=None):
+        self.m_local, self.n, self.world, self.group = m_local, n, world, group
+        self._local = self._top = None
+        if local_reduce is None:
+            self._local = Tsqr(m_local, n)
+            self._top = Tsqr(world * n, n, strips=1) if world > 1 else None
+        self.local_reduce = local_reduce or self._cuda_local
+        self.top_reduce = top_reduce or self._cuda_top
+
+    def _cuda_local(self, A, R):
+        import torch
+        self._local.factor(A.data_ptr(), self.m_local, R.data_ptr(), torch.cuda.current_stream().cuda_stream)
+
+    def _cuda_top(self, stack, R):
+        import torch
+        self._top.factor(stack.data_ptr(), self.world * self.n, R.data_ptr(), torch.cuda.current_stream().cuda_stream)
+
+    def factor(self, A, R):
+        """A: this rank's (n, m_local) tensor = column-major m_local x n block, overwritten with its reflectors;
+        R: (n, n) tensor receiving the final factor (column-major, [column, row]).  Returns the local R factor."""
+        import torch
+        R_local = torch.empty_like(R)
+        self.local_reduce(A, R_local)
+        if self.world == 1:
+            R.copy_(R_local)
+            return R_local
+        stack = tsqr_gather_stack(R_local, self.world, self.group)
+        self.top_reduce(stack, R)
+        self.stack = stack                      # the top tree's reflectors (kept: part of the implicit Q)
+        return R_local
+
+    def close(self):
+        for t in (self._local, self._top):
+            if t is not None:
+                t.close()
+
+
 def dist_connect_local(ranks):
     arr = (C.c_void_p * len(ranks))(*[r._h for r in ranks])
     check(lib().b200qr_dist_connect_local(arr, len(ranks)), "b200qr_dist_connect_local")

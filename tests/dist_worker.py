@@ -93,3 +93,43 @@ def run(rank, world, port, m, n, G, result_path):
         dist.barrier()
     finally:
         dist.destroy_process_group()
+
+
+def run_tsqr(rank, world, port, m_local, n, result_path):
+    """Multi-GPU TSQR exchange (TsqrDist) over gloo with the ORACLE's flat-tree tiled QR standing in for the CUDA
+    engines: every rank reduces its own row block, the R factors are all-gathered, every rank reduces the stack.  All
+    ranks must end with the same R, equal to float64 LAPACK's R of the whole matrix up to row signs."""
+    import torch
+    import torch.distributed as dist
+    import pyoracle as po
+    import gpu_tiled_qr_decomposition_b200 as q
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        def oracle_reduce(rows):
+            def fn(A, R):                                   # A: (n, rows) tensor = column-major rows x n
+                out, _ = po.tiled_qr(np.ascontiguousarray(A.numpy()), rows, n)
+                R.copy_(torch.from_numpy(np.ascontiguousarray(np.triu(out[:, :n].T).T)))   # [c, r], zero below the diagonal
+            return fn
+        rng = np.random.default_rng(1234)                   # same full matrix on every rank
+        full = rng.uniform(-1, 1, size=(n, m_local * world)).astype(np.float32)
+        A = torch.from_numpy(np.ascontiguousarray(full[:, rank * m_local:(rank + 1) * m_local]))
+        R = torch.zeros((n, n), dtype=torch.float32)
+        td = q.TsqrDist(m_local, n, world, local_reduce=oracle_reduce(m_local), top_reduce=oracle_reduce(world * n))
+        td.factor(A, R)
+        Rm = R.numpy().T.astype(np.float64)                 # (row, col)
+        ok = np.count_nonzero(np.tril(Rm, -1)) == 0
+        R64 = np.linalg.qr(full.T.astype(np.float64), mode="r")
+        sgn = np.sign(np.diag(R64)) * np.sign(np.diag(Rm))
+        ok = ok and np.max(np.abs(Rm - sgn[:, None] * R64)) <= 1e-4 * np.max(np.abs(R64))
+        allR = [torch.empty_like(R) for _ in range(world)]
+        dist.all_gather(allR, R)
+        ok = ok and all(torch.equal(allR[0], x) for x in allR)
+        flag = torch.tensor([1 if ok else 0])
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            with open(result_path, "w") as f:
+                f.write("OK" if flag.item() == 1 else "MISMATCH")
+    finally:
+        dist.destroy_process_group()

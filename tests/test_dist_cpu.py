@@ -40,3 +40,13 @@ def test_rank_tickets_partition(qr):
                 cnt += len(sw)
                 pan += pa.tolist()
             assert cnt == total and sorted(pan) == list(range(min(M, N)))
+
+
+@pytest.mark.parametrize("m_local,n,world", [(512, 128, 2), (256, 64, 3)])
+def test_tsqr_exchange_gloo(qr, po, tmp_path, m_local, n, world):
+    """configs[3] across ranks: local reduction, all-gather of the R factors, redundant top reduction (TsqrDist)."""
+    import torch.multiprocessing as mp
+    import dist_worker
+    res = str(tmp_path / "result.txt")
+    mp.spawn(dist_worker.run_tsqr, args=(world, free_port(), m_local, n, res), nprocs=world, join=True)
+    assert open(res).read() == "OK"

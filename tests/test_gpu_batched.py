@@ -112,3 +112,35 @@ def test_tsqr_streaming_r_factor(cuda, qr, m, n, strips):
     assert (torch.max(torch.abs(Rm - s[:, None] * R64)) / torch.max(torch.abs(R64))).item() <= 1e-4
     # the reflectors left in place are bounded (|v| <= 1 elementwise for a Householder vector scaled by its pivot)
     assert torch.isfinite(d).all() and d.abs().max().item() <= 1.0 + 1e-6
+
+
+def test_tsqr_streaming_reflectors_reproduce_r(cuda, qr):
+    """One strip: the reflector blocks left in place ARE the implicit Q.  Replaying them in float64 on [0; A] (the
+    TSQRT recurrence starts from an empty triangle on top of the strip: v_c = [e_c; V2(:, c)] per block of 128 rows,
+    tau_c = 2 / (1 + |V2(:, c)|^2), qrdecomp.c:660-664) must give [R; 0] with the R the engine returned."""
+    torch = cuda
+    m, n, rb = 1024, 64, 128
+    g = torch.Generator(device="cuda").manual_seed(21)
+    A = torch.rand((n, m), generator=g, device="cuda", dtype=torch.float32) * 2 - 1
+    d = A.clone()
+    h = C.c_void_p()
+    qr.check(qr.lib().b200qr_tsqr_create_streaming(C.byref(h), m, n, 1))
+    R = torch.zeros((n, n), dtype=torch.float32, device="cuda")
+    qr.check(qr.lib().b200qr_tsqr_factor(h, C.c_void_p(d.data_ptr()), m, C.c_void_p(R.data_ptr()),
+                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    qr.lib().b200qr_tsqr_destroy(h)
+    V = d.t().double()                                   # (m, n): block rows of reflectors
+    top = torch.zeros((n, n), dtype=torch.float64, device="cuda")
+    bot = A.t().double().clone()                         # (m, n)
+    for blk in range(m // rb):
+        rows = slice(blk * rb, (blk + 1) * rb)
+        for c in range(n):
+            v2 = V[rows, c]
+            tau = 2.0 / (1.0 + torch.dot(v2, v2))
+            w = tau * (top[c, :] + v2 @ bot[rows, :])
+            top[c, :] -= w
+            bot[rows, :] -= torch.outer(v2, w)
+    scale = top.abs().max().item()
+    assert bot.abs().max().item() <= 2e-5 * scale        # everything below the triangle is annihilated
+    assert (top - R.t().double()).abs().max().item() <= 2e-5 * scale

@@ -76,3 +76,39 @@ def test_tensor_core_engine_on_two_real_gpus(cuda):
                        capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "single-GPU variant 5" in r.stdout and "identical: True" in r.stdout, r.stdout[-2000:]
+
+
+def test_tsqr_split_over_two_real_gpus(cuda):
+    """configs[3] on two GPUs (TsqrDist: local streaming reduction, NCCL all-gather of the R factors, redundant top
+    reduction): same R on both ranks, R^T R = A^T A.  Needs two visible GPUs (skipped on a one-GPU box)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    torch = cuda
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541",
+                        os.path.join(root, "tools", "bench_tsqr_dist.py"), "262144", "256"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = json.loads([x for x in r.stdout.splitlines() if x.startswith("{")][-1])
+    assert line["same_R_on_all_ranks"] and line["gram_rel_err"] <= 50 * float(np.finfo(np.float32).eps), line
+
+
+def test_tsqr_dist_single_rank(cuda, qr):
+    """TsqrDist with one rank = the plain streaming plan."""
+    torch = cuda
+    m, n = 65536, 128
+    g = torch.Generator(device="cuda").manual_seed(9)
+    A0 = torch.rand((n, m), generator=g, device="cuda", dtype=torch.float32) * 2 - 1
+    A, R = A0.clone(), torch.zeros((n, n), device="cuda")
+    td = qr.TsqrDist(m, n, 1)
+    td.factor(A, R)
+    torch.cuda.synchronize()
+    td.close()
+    Rm, Ad = R.t().double(), A0.t().double()
+    G = Ad.t() @ Ad
+    assert (torch.linalg.norm(Rm.t() @ Rm - G) / torch.linalg.norm(G)).item() <= 50 * float(np.finfo(np.float32).eps)
