@@ -31,7 +31,7 @@ EXPORTS = (
     "b200qr_dist_owner", "b200qr_dist_grid", "b200qr_dist_variant", "b200qr_dist_read_trace", "b200qr_dist_tile_tasks", "b200qr_dist_reset", "b200qr_dist_factor",
     "b200qr_dist_connect_local", "b200qr_dist_factor_group",
     "b200qr_batched_workspace_floats", "b200qr_batched_factor", "b200qr_batched_last_cuda_error",
-    "b200qr_tsqr_create", "b200qr_tsqr_create_streaming", "b200qr_tsqr_destroy", "b200qr_tsqr_levels", "b200qr_tsqr_factor",
+    "b200qr_tsqr_create", "b200qr_tsqr_create_streaming", "b200qr_tsqr_stream_block_rows", "b200qr_tsqr_destroy", "b200qr_tsqr_levels", "b200qr_tsqr_factor",
     "b200qr_apply_q", "b200qr_release_cache", "cudaQRTask", "cudaQRFull", "testDAPP", "doCUDADAPP",
 )
 
@@ -135,6 +135,7 @@ def lib():
         L.b200qr_batched_factor.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int, vp, vp, vp]
         L.b200qr_tsqr_create.argtypes = [C.POINTER(vp), C.c_longlong, C.c_int, C.c_int, C.c_int]
         L.b200qr_tsqr_create_streaming.argtypes = [C.POINTER(vp), C.c_longlong, C.c_int, C.c_int]
+        L.b200qr_tsqr_stream_block_rows.argtypes = [vp]
         L.b200qr_tsqr_destroy.argtypes = [vp]
         L.b200qr_tsqr_levels.argtypes = [vp]
         L.b200qr_tsqr_factor.argtypes = [vp, vp, C.c_longlong, vp, vp]
@@ -383,8 +384,8 @@ class TsqrDist:
     Every rank reduces its block to an n x n R factor (streaming engine), the factors are all-gathered -- the path's one
     real exchange step, W x 256 KB at n = 256 -- and every rank reduces the stack of W factors redundantly, so all ranks
     end with the same R.  The implicit Q is the rank's leaf reflectors (in place in its block) plus the two trees.
-    `local_reduce(A, R)` / `top_reduce(stack, R)` default to the CUDA plans; the gloo CPU test injects the oracle to
-    exercise the exchange without a GPU."""
+    `local_reduce(A, R)` / `top_reduce(stack, R)` are the CUDA plans (there is no CPU implementation here); the gloo
+    test of the exchange step passes its own stand-ins for them, since that test runs without a GPU."""
 
     def __init__(self, m_local, n, world, group=None, local_reduce=None, top_reduce=None):
         self.m_local, self.n, self.world, self.group = m_local, n, world, group

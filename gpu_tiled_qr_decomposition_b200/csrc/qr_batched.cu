@@ -221,44 +221,48 @@ __global__ void __launch_bounds__(128) apply_q_kernel(const float *A, int ldm, c
 // ---------------------------------------------------------------------------------------------
 // Streaming TSQR: the TSQRT recurrence (qrdecomp.c:689-721 STSQRF, 1243-1272 calcvkDouble, 647-687
 // updateDoubleQ_WY) with the tile as wide as the matrix.  One CTA owns a strip of rows and walks down it in blocks
-// of SRB rows, the n x n triangle R resident in shared memory (packed by rows), thread = matrix column with its SRB
-// elements of the block in registers.  Per reflector c: the owner thread derives (1/piv, tau) from R(c,c) and its
-// column's sum of squares and broadcasts the column through shared memory; every thread j >= c does one dot product
-// and one axpy of length SRB; the reflector V2(:,c) = x / piv replaces column c of the block in place.  The n
-// reflectors of a block are a flat-tree TSQRT step exactly like the reference's, only n columns wide instead of 32;
-// the strips' R factors are stacked and reduced by the same kernel, eight at a time, until one is left.
-// Versus the leaf-batch tree above this removes the 32-column tile chains (8 us per tile on one warp, the other seven
-// waiting their turn): a block of 128 x 256 costs ~256 x 500 cycles with all eight warps busy.
-constexpr int SRB = 128;                    // rows per block
-constexpr int STREAM_FANIN = 8;             // R factors per strip in the reduction levels
+// of SRB rows; thread = matrix column, its SRB elements of the block in registers.  Per reflector c: the owner thread
+// derives (1/piv, tau) from R(c,c) and its column's sum of squares and broadcasts the column through shared memory;
+// every thread j >= c does one dot product and one axpy of length SRB; the reflector V2(:,c) = x / piv replaces
+// column c of the block in place.  The n reflectors of a block are a flat-tree TSQRT step exactly like the
+// reference's, only n columns wide instead of 32.  The strips' R factors are stacked and reduced by the leaf-batch
+// tree above.
+//
+// What bounds it (ncu, profiles/r1_tsqr_strip_summary.txt): the n reflectors of a block are strictly serial and one
+// step is a chain of dependent latencies -- broadcast, dot, update, the next owner's sum of squares, rsqrt / rcp,
+// barrier: ~1050 cycles for 64 rows, 48 % of all warp samples wait at the barrier, the FMA pipe is 18 % busy.  So
+// the triangle R lives in global memory (L2-resident, 131 KB per strip; a thread only ever touches its own column
+// of it and prefetches row c + 1 during step c), which leaves shared memory nearly empty and lets TWO CTAs share an
+// SM (128 registers each): two independent chains per SM.
 
 struct StripArgs {
     float *A;                               // rows x n, column-major
     long long ldm, rows, rows_per_strip, blocks_per_strip;
     int n;
     float *tau;                             // [strip * blocks_per_strip + block][n]
+    float *Rws;                             // [strip][n (n + 1) / 2]: the strip's triangle, packed by rows, zero on entry
     float *Rout;                            // strip s writes its R at rows s*n .. of a column-major stack
     long long ldr;
 };
 
-__global__ void __launch_bounds__(256, 1) tsqr_strip_kernel(const StripArgs a)
+// SRB = rows per block (a thread's block column lives in registers), MINB = CTAs per SM the register budget allows:
+// <48, 2> is the default (117 registers, no spills; 64 rows spill at 128), <32, 3> trades block height for a third chain.
+template <int SRB, int MINB>
+__global__ void __launch_bounds__(256, MINB) tsqr_strip_kernel(const StripArgs a)
 {
-    extern __shared__ __align__(16) float ssm[];
+    __shared__ __align__(16) float xs[2 * SRB];             // two broadcast slots
+    __shared__ float hs[4];                                 // two slots of {1/piv, tau}
     const int n = a.n, j = threadIdx.x, warp = j >> 5;
-    const int rt_floats = n * (n + 1) / 2;
-    float *Rt = ssm;                                        // (c, col) at c*n - c*(c-1)/2 + (col - c)
-    float *xs = ssm + ((rt_floats + 3) & ~3);               // two broadcast slots of SRB floats
-    float *hs = xs + 2 * SRB;                               // two slots of {1/piv, tau}
-    for (int e = j; e < rt_floats; e += n) Rt[e] = 0.f;
+    float *Rg = a.Rws + (size_t)blockIdx.x * (n * (n + 1) / 2);    // (c, col) at c*n - c*(c-1)/2 + (col - c)
     const long long row0 = (long long)blockIdx.x * a.rows_per_strip;
     long long row1 = row0 + a.rows_per_strip;
     if (row1 > a.rows) row1 = a.rows;
     float *col = a.A + (size_t)j * a.ldm;
     float *tau_out = a.tau + (size_t)blockIdx.x * a.blocks_per_strip * n;
-    __syncthreads();
 
     for (long long r0 = row0; r0 < row1; r0 += SRB, tau_out += n) {
         const int nr = (int)(row1 - r0 < SRB ? row1 - r0 : SRB);     // a multiple of 4
+        float rc_next = __ldcg(Rg + j);                     // R(0, j): this thread's own store of the previous block
         float b[SRB];
 #pragma unroll
         for (int r = 0; r < SRB; r += 4) {
@@ -282,36 +286,41 @@ __global__ void __launch_bounds__(256, 1) tsqr_strip_kernel(const StripArgs a)
             float *x = xs + (c & 1) * SRB;
             float *h2 = hs + (c & 1) * 2;
             const int off = c * n - (c * (c - 1)) / 2;
+            const float rc = rc_next;                       // R(c, j), valid for j >= c
             if (j == c) {                                   // owner: broadcast the column and its Householder scalars
 #pragma unroll
                 for (int r = 0; r < SRB; r += 4) *reinterpret_cast<float4 *>(x + r) = make_float4(b[r], b[r + 1], b[r + 2], b[r + 3]);
-                const HouseScalars h = house_scalars(Rt[off], ssq);
+                const HouseScalars h = house_scalars(rc, ssq);
                 h2[0] = h.inv; h2[1] = h.tau;
                 tau_out[c] = h.tau;
             }
+            if (j > c) rc_next = __ldcg(Rg + off + (n - c) + (j - c - 1));     // R(c + 1, j): in flight during this step
             __syncthreads();
             const float inv = h2[0], tau = h2[1];
+            // the reflector replaces column c of the block
+            {
+                float *vcol = a.A + (size_t)c * a.ldm + r0;
+                for (int t = j; t < nr; t += n) vcol[t] = x[t] * inv;
+            }
             if (j >= c) {
                 // beta = tau (R(c,j) + v' B(:,j)),  v = x / piv
-                float s[16];
+                float s[8];
 #pragma unroll
-                for (int i = 0; i < 16; i += 4) {
+                for (int i = 0; i < 8; i += 4) {
                     const float4 xv = *reinterpret_cast<const float4 *>(x + i);
                     s[i] = b[i] * xv.x; s[i + 1] = b[i + 1] * xv.y; s[i + 2] = b[i + 2] * xv.z; s[i + 3] = b[i + 3] * xv.w;
                 }
 #pragma unroll
-                for (int r = 16; r < SRB; r += 16)
+                for (int r = 8; r < SRB; r += 8)
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
+                    for (int i = 0; i < 8; i += 4) {
                         const float4 xv = *reinterpret_cast<const float4 *>(x + r + i);
                         s[i] = fmaf(b[r + i], xv.x, s[i]); s[i + 1] = fmaf(b[r + i + 1], xv.y, s[i + 1]);
                         s[i + 2] = fmaf(b[r + i + 2], xv.z, s[i + 2]); s[i + 3] = fmaf(b[r + i + 3], xv.w, s[i + 3]);
                     }
-                const float d = (((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]))) +
-                                (((s[8] + s[9]) + (s[10] + s[11])) + ((s[12] + s[13]) + (s[14] + s[15])));
-                const float rc = Rt[off + j - c];
+                const float d = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
                 const float beta = tau * fmaf(inv, d, rc);
-                Rt[off + j - c] = rc - beta;
+                __stcg(Rg + off + j - c, rc - beta);
                 if (j > c) {
                     const float g = -beta * inv;
 #pragma unroll
@@ -323,14 +332,10 @@ __global__ void __launch_bounds__(256, 1) tsqr_strip_kernel(const StripArgs a)
                     if (warp == ((c + 1) >> 5)) ssq = sumsq();      // the next owner lives in this warp
                 }
             }
-            // the reflector replaces column c of the block
-            float *vcol = a.A + (size_t)c * a.ldm + r0;
-            for (int t = j; t < nr; t += n) vcol[t] = x[t] * inv;
         }
     }
-    __syncthreads();
     float *rcol = a.Rout + (size_t)j * a.ldr + (size_t)blockIdx.x * n;
-    for (int c = 0; c < n; ++c) rcol[c] = (c <= j) ? Rt[c * n - (c * (c - 1)) / 2 + (j - c)] : 0.f;
+    for (int c = 0; c < n; ++c) rcol[c] = (c <= j) ? __ldcg(Rg + c * n - (c * (c - 1)) / 2 + (j - c)) : 0.f;
 }
 
 }  // namespace qrb200
@@ -374,9 +379,11 @@ struct b200qr_tsqr_s {
     float *d_leaf_tau = nullptr;
     struct Level { long long count; int nfull, rest; float *stack = nullptr, *tau = nullptr; };
     std::vector<Level> levels;          // reduction levels: `count` R factors in, nfull + (rest > 0) out
-    // streaming engine (b200qr_tsqr_create_streaming): level 0 walks the matrix, the others the stacked R factors
-    struct SLevel { long long rows, rows_per_strip, blocks_per_strip; int strips; float *tau = nullptr, *out = nullptr; };
-    std::vector<SLevel> slevels;        // `out` = this level's R stack (strips*n x n); the last level writes dR
+    // streaming engine (b200qr_tsqr_create_streaming): strips of rows -> one R factor each, stacked in levels[0].stack
+    // (or written to dR when there is one strip); the levels above reduce them
+    int strips = 0, srb = 48;
+    long long rows_per_strip = 0, blocks_per_strip = 0;
+    float *d_stream_tau = nullptr, *d_rws = nullptr;
     bool streaming = false;
 };
 
@@ -421,6 +428,7 @@ int b200qr_apply_q(const float *dA, int m, int n, int ldm, const float *dTauComp
 }
 
 // ---- TSQR ------------------------------------------------------------------------------------
+static int build_levels(b200qr_tsqr_s *t, long long count);
 // Level structure: `count` R factors (n x n) are stacked into a (count*n) x n matrix and factored in
 // groups of `fanin` consecutive factors (one batched problem of fanin*n rows each; a shorter last
 // group of >= 2 factors is its own problem, a single left-over factor passes through).  The group
@@ -437,55 +445,57 @@ int b200qr_tsqr_create(b200qr_tsqr_t *out, long long m, int n, int leaf_rows, in
     auto fail = [&]() { b200qr_tsqr_destroy(t); return B200QR_ENOMEM; };
     if (cudaMalloc(&t->d_counter, sizeof(int)) != cudaSuccess) return fail();
     if (cudaMalloc(&t->d_leaf_tau, sizeof(float) * (size_t)nleaf * q * (leaf_rows / TB) * TB) != cudaSuccess) return fail();
-    long long count = nleaf;
+    if (build_levels(t, nleaf) != B200QR_OK) return fail();
+    *out = t;
+    return B200QR_OK;
+}
+
+// Level structure shared by both engines: `count` R factors in, fanin at a time
+static int build_levels(b200qr_tsqr_s *t, long long count)
+{
+    const int n = t->n, q = n / TB, fanin = t->fanin;
     while (count > 1) {
         b200qr_tsqr_s::Level L;
         L.count = count;
         L.nfull = (int)(count / fanin);
         L.rest = (int)(count % fanin);
-        if (cudaMalloc(&L.stack, sizeof(float) * (size_t)count * n * n) != cudaSuccess) return fail();
+        if (cudaMalloc(&L.stack, sizeof(float) * (size_t)count * n * n) != cudaSuccess) return B200QR_ENOMEM;
         // tau: q * (rows/32) * 32 floats per problem = q * rows floats
         size_t taufl = (size_t)L.nfull * q * fanin * n + (size_t)q * (L.rest > 0 ? L.rest : 1) * n;
-        if (cudaMalloc(&L.tau, sizeof(float) * taufl) != cudaSuccess) { cudaFree(L.stack); return fail(); }
+        if (cudaMalloc(&L.tau, sizeof(float) * taufl) != cudaSuccess) { cudaFree(L.stack); return B200QR_ENOMEM; }
         t->levels.push_back(L);
         count = L.nfull + (L.rest > 0 ? 1 : 0);
     }
-    *out = t;
     return B200QR_OK;
 }
 
-// Streaming engine: `strips` CTAs (<= 0: one per SM) each reduce a contiguous strip of rows to one R factor; the
-// factors are stacked and reduced eight per CTA until one is left.  m % 32 == 0, n % 32 == 0, n <= 256.
+// Streaming engine: `strips` CTAs (<= 0: two per SM, which is what fits) each reduce a contiguous strip of rows to one
+// R factor; the factors are reduced by the leaf-batch tree, four at a time.  m % 32 == 0, n % 32 == 0, n <= 256.
 int b200qr_tsqr_create_streaming(b200qr_tsqr_t *out, long long m, int n, int strips)
 {
     if (!out || n <= 0 || n % TB || n > BQ * TB || m <= 0 || m % TB) return B200QR_EINVAL;
-    if (strips <= 0) {
+    const bool strips_auto = strips <= 0;
+    int sms = 0;
+    if (strips_auto) {
         int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&strips, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
             return B200QR_ECUDA;
     }
     b200qr_tsqr_s *t = new b200qr_tsqr_s;
-    t->m = m; t->n = n; t->leaf_rows = 0; t->fanin = STREAM_FANIN; t->streaming = true;
+    t->m = m; t->n = n; t->leaf_rows = 0; t->fanin = 4; t->streaming = true;
     auto fail = [&]() { b200qr_tsqr_destroy(t); return B200QR_ENOMEM; };
-    long long rows = m;
-    long long want = strips;
-    for (;;) {
-        b200qr_tsqr_s::SLevel L;
-        L.rows = rows;
-        long long rps = (rows + want - 1) / want;
-        rps = (rps + SRB - 1) / SRB * SRB;
-        L.rows_per_strip = rps;
-        L.blocks_per_strip = rps / SRB;
-        L.strips = (int)((rows + rps - 1) / rps);
-        if (cudaMalloc(&L.tau, sizeof(float) * (size_t)L.strips * L.blocks_per_strip * n) != cudaSuccess) return fail();
-        if (L.strips > 1 && cudaMalloc(&L.out, sizeof(float) * (size_t)L.strips * n * n) != cudaSuccess) { cudaFree(L.tau); return fail(); }
-        t->slevels.push_back(L);
-        if (L.strips == 1) break;
-        rows = (long long)L.strips * n;
-        want = (L.strips + STREAM_FANIN - 1) / STREAM_FANIN;
-    }
-    const int smem = (((n * (n + 1) / 2 + 3) & ~3) + 2 * SRB + 4) * (int)sizeof(float);
-    if (cudaFuncSetAttribute(tsqr_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return fail();
+    if (const char *e = getenv("QRB200_TSQR_RB")) { const int v = atoi(e); if (v == 32 || v == 48 || v == 64) t->srb = v; }
+    const int SRB = t->srb;
+    if (strips_auto) strips = sms * (SRB == 32 ? 3 : 2);
+    long long rps = (m + strips - 1) / strips;
+    rps = (rps + SRB - 1) / SRB * SRB;
+    t->rows_per_strip = rps;
+    t->blocks_per_strip = rps / SRB;
+    t->strips = (int)((m + rps - 1) / rps);
+    if (cudaMalloc(&t->d_counter, sizeof(int)) != cudaSuccess) return fail();
+    if (cudaMalloc(&t->d_stream_tau, sizeof(float) * (size_t)t->strips * t->blocks_per_strip * n) != cudaSuccess) return fail();
+    if (cudaMalloc(&t->d_rws, sizeof(float) * (size_t)t->strips * (n * (n + 1) / 2)) != cudaSuccess) return fail();
+    if (build_levels(t, t->strips) != B200QR_OK) return fail();
     *out = t;
     return B200QR_OK;
 }
@@ -495,12 +505,14 @@ int b200qr_tsqr_destroy(b200qr_tsqr_t t)
     if (!t) return B200QR_EINVAL;
     cudaFree(t->d_counter); cudaFree(t->d_leaf_tau);
     for (auto &L : t->levels) { cudaFree(L.stack); cudaFree(L.tau); }
-    for (auto &L : t->slevels) { cudaFree(L.out); cudaFree(L.tau); }
+    cudaFree(t->d_stream_tau); cudaFree(t->d_rws);
     delete t;
     return B200QR_OK;
 }
 
-int b200qr_tsqr_levels(b200qr_tsqr_t t) { return t ? (int)(t->streaming ? t->slevels.size() : t->levels.size()) : B200QR_EINVAL; }
+int b200qr_tsqr_stream_block_rows(b200qr_tsqr_t t) { return t && t->streaming ? t->srb : B200QR_EINVAL; }
+
+int b200qr_tsqr_levels(b200qr_tsqr_t t) { return t ? (int)t->levels.size() + (t->streaming ? 1 : 0) : B200QR_EINVAL; }
 
 // Factor the m x n matrix dA (column-major, ldm) in place (leaf reflectors) and write the n x n
 // upper-triangular R (column-major, leading dimension n) to dR.  Asynchronous on `stream`.
@@ -508,34 +520,37 @@ int b200qr_tsqr_factor(b200qr_tsqr_t t, float *dA, long long ldm, float *dR, voi
 {
     if (!t || !dA || !dR || ldm < t->m || (ldm & 3) || ldm > 0x7fffffffLL) return B200QR_EINVAL;
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (t->streaming) {
-        const int n = t->n;
-        const int smem = (((n * (n + 1) / 2 + 3) & ~3) + 2 * SRB + 4) * (int)sizeof(float);
-        float *in = dA;
-        long long ld = ldm;
-        for (auto &L : t->slevels) {
-            StripArgs a;
-            a.A = in; a.ldm = ld; a.rows = L.rows; a.rows_per_strip = L.rows_per_strip; a.blocks_per_strip = L.blocks_per_strip;
-            a.n = n; a.tau = L.tau;
-            a.Rout = L.strips > 1 ? L.out : dR;
-            a.ldr = L.strips > 1 ? (long long)L.strips * n : n;
-            tsqr_strip_kernel<<<L.strips, n, smem, stream>>>(a);
-            CKB(cudaGetLastError());
-            in = L.out; ld = (long long)L.strips * n;
-        }
-        return B200QR_OK;
-    }
     const int n = t->n, q = n / TB, fanin = t->fanin;
-    long long count = t->m / t->leaf_rows;
-    int rc = batched_launch(dA, t->leaf_rows, n, (int)ldm, t->leaf_rows, (int)count, t->d_leaf_tau, t->d_counter, stream);
-    if (rc != B200QR_OK) return rc;
+    int rc;
     const float *src = dA;
     long long src_stride = t->leaf_rows;
     int src_ld = (int)ldm;
+    bool first_stack_filled = false;
+    if (t->streaming) {
+        CKB(cudaMemsetAsync(t->d_rws, 0, sizeof(float) * (size_t)t->strips * (n * (n + 1) / 2), stream));
+        StripArgs a;
+        a.A = dA; a.ldm = ldm; a.rows = t->m; a.rows_per_strip = t->rows_per_strip; a.blocks_per_strip = t->blocks_per_strip;
+        a.n = n; a.tau = t->d_stream_tau; a.Rws = t->d_rws;
+        a.Rout = t->strips > 1 ? t->levels[0].stack : dR;             // the strips' triangles ARE the first level's stack
+        a.ldr = t->strips > 1 ? (long long)t->strips * n : n;
+        if (t->srb == 32) tsqr_strip_kernel<32, 3><<<t->strips, n, 0, stream>>>(a);
+        else if (t->srb == 64) tsqr_strip_kernel<64, 2><<<t->strips, n, 0, stream>>>(a);
+        else tsqr_strip_kernel<48, 2><<<t->strips, n, 0, stream>>>(a);
+        CKB(cudaGetLastError());
+        if (t->strips == 1) return B200QR_OK;
+        first_stack_filled = true;
+    } else {
+        long long count = t->m / t->leaf_rows;
+        rc = batched_launch(dA, t->leaf_rows, n, (int)ldm, t->leaf_rows, (int)count, t->d_leaf_tau, t->d_counter, stream);
+        if (rc != B200QR_OK) return rc;
+    }
     for (auto &L : t->levels) {
         const int sld = (int)(L.count * n);
-        gather_r_kernel<<<1024, 256, 0, stream>>>(src, src_stride, src_ld, n, (int)L.count, L.stack);
-        CKB(cudaGetLastError());
+        if (!first_stack_filled) {
+            gather_r_kernel<<<1024, 256, 0, stream>>>(src, src_stride, src_ld, n, (int)L.count, L.stack);
+            CKB(cudaGetLastError());
+        }
+        first_stack_filled = false;
         if (L.nfull > 0) {
             rc = batched_launch(L.stack, fanin * n, n, sld, (long long)fanin * n, L.nfull, L.tau, t->d_counter, stream);
             if (rc != B200QR_OK) return rc;

@@ -165,11 +165,13 @@ int b200qr_batched_last_cuda_error(void);
  * b200qr_batched_factor once more (see bench.py / tests).                                       */
 typedef struct b200qr_tsqr_s *b200qr_tsqr_t;
 int b200qr_tsqr_create(b200qr_tsqr_t *t, long long m, int n, int leaf_rows, int fanin);
-/* Streaming engine for the same job (same b200qr_tsqr_factor / _destroy): `strips` CTAs (<= 0: one per SM) each walk a
- * contiguous strip of rows in blocks of 128, the n x n triangle resident in shared memory -- the reference's TSQRT
- * recurrence (qrdecomp.c:689-721) with the tile as wide as the matrix -- and the strips' R factors are reduced by the
- * same kernel, eight per CTA, until one is left.  Reflectors stay in dA (blocks of 128 x n) and in the plan (tree). */
+/* Streaming engine for the same job (same b200qr_tsqr_factor / _destroy): `strips` CTAs (<= 0: two per SM) each walk a
+ * contiguous strip of rows in blocks of b200qr_tsqr_stream_block_rows(t) rows (48) -- the reference's TSQRT recurrence
+ * (qrdecomp.c:689-721) with the tile as wide as the matrix, thread = matrix column, the strip's n x n triangle in L2 --
+ * and the strips' R factors are reduced by the leaf-batch tree, four at a time.  Reflectors stay in dA (one block of
+ * rows x n per TSQRT step, strips of ceil(m / strips) rows rounded up to whole blocks) and in the plan (tree). */
 int b200qr_tsqr_create_streaming(b200qr_tsqr_t *t, long long m, int n, int strips);
+int b200qr_tsqr_stream_block_rows(b200qr_tsqr_t t);
 int b200qr_tsqr_destroy(b200qr_tsqr_t t);
 int b200qr_tsqr_levels(b200qr_tsqr_t t);
 int b200qr_tsqr_factor(b200qr_tsqr_t t, float *dA, long long ldm, float *dR, void *stream);

@@ -116,15 +116,17 @@ def test_tsqr_streaming_r_factor(cuda, qr, m, n, strips):
 
 def test_tsqr_streaming_reflectors_reproduce_r(cuda, qr):
     """One strip: the reflector blocks left in place ARE the implicit Q.  Replaying them in float64 on [0; A] (the
-    TSQRT recurrence starts from an empty triangle on top of the strip: v_c = [e_c; V2(:, c)] per block of 128 rows,
+    TSQRT recurrence starts from an empty triangle on top of the strip: v_c = [e_c; V2(:, c)] per block of rows,
     tau_c = 2 / (1 + |V2(:, c)|^2), qrdecomp.c:660-664) must give [R; 0] with the R the engine returned."""
     torch = cuda
-    m, n, rb = 1024, 64, 128
+    m, n = 1536, 64
     g = torch.Generator(device="cuda").manual_seed(21)
     A = torch.rand((n, m), generator=g, device="cuda", dtype=torch.float32) * 2 - 1
     d = A.clone()
     h = C.c_void_p()
     qr.check(qr.lib().b200qr_tsqr_create_streaming(C.byref(h), m, n, 1))
+    rb = qr.lib().b200qr_tsqr_stream_block_rows(h)
+    assert rb > 0 and m % rb == 0
     R = torch.zeros((n, n), dtype=torch.float32, device="cuda")
     qr.check(qr.lib().b200qr_tsqr_factor(h, C.c_void_p(d.data_ptr()), m, C.c_void_p(R.data_ptr()),
                                          C.c_void_p(torch.cuda.current_stream().cuda_stream)))

@@ -98,5 +98,9 @@ if __name__ == "__main__":
         for leaf in (512, 2048):
             tsqr(leaf=leaf)
     if which in ("all", "tsqr", "stream"):
-        for strips in (0, 296, 592):
-            tsqr_streaming(strips=strips)
+        for rb in ("48", "32", "64"):                 # block rows / CTAs per SM: <48, 2> (default), <32, 3>, <64, 2>
+            os.environ["QRB200_TSQR_RB"] = rb
+            print("QRB200_TSQR_RB=" + rb, end="  ")
+            tsqr_streaming(strips=0)
+        os.environ.pop("QRB200_TSQR_RB", None)
+        tsqr_streaming(m=1048576)
