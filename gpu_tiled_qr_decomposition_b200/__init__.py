@@ -31,7 +31,7 @@ EXPORTS = (
     "b200qr_dist_owner", "b200qr_dist_grid", "b200qr_dist_variant", "b200qr_dist_read_trace", "b200qr_dist_tile_tasks", "b200qr_dist_reset", "b200qr_dist_factor",
     "b200qr_dist_connect_local", "b200qr_dist_factor_group",
     "b200qr_batched_workspace_floats", "b200qr_batched_factor", "b200qr_batched_last_cuda_error",
-    "b200qr_tsqr_create", "b200qr_tsqr_create_streaming", "b200qr_tsqr_stream_block_rows", "b200qr_tsqr_destroy", "b200qr_tsqr_levels", "b200qr_tsqr_factor",
+    "b200qr_tsqr_create", "b200qr_tsqr_create_streaming", "b200qr_tsqr_stream_block_rows", "b200qr_tsqr_create_rstack", "b200qr_tsqr_destroy", "b200qr_tsqr_levels", "b200qr_tsqr_factor",
     "b200qr_apply_q", "b200qr_release_cache", "cudaQRTask", "cudaQRFull", "testDAPP", "doCUDADAPP",
 )
 
@@ -136,6 +136,7 @@ def lib():
         L.b200qr_tsqr_create.argtypes = [C.POINTER(vp), C.c_longlong, C.c_int, C.c_int, C.c_int]
         L.b200qr_tsqr_create_streaming.argtypes = [C.POINTER(vp), C.c_longlong, C.c_int, C.c_int]
         L.b200qr_tsqr_stream_block_rows.argtypes = [vp]
+        L.b200qr_tsqr_create_rstack.argtypes = [C.POINTER(vp), C.c_int, C.c_int]
         L.b200qr_tsqr_destroy.argtypes = [vp]
         L.b200qr_tsqr_levels.argtypes = [vp]
         L.b200qr_tsqr_factor.argtypes = [vp, vp, C.c_longlong, vp, vp]
@@ -338,10 +339,12 @@ class Tsqr:
     """Tall-skinny QR of an m x n matrix, n <= 256 (b200qr_tsqr_*).  Default: the streaming engine (strips of rows, the
     n x n triangle resident in shared memory); leaf_rows > 0 selects the leaf-batch tree (reference tile layout per leaf)."""
 
-    def __init__(self, m, n, strips=0, leaf_rows=0, fanin=4):
+    def __init__(self, m, n, strips=0, leaf_rows=0, fanin=4, rstack=0):
         self.m, self.n = m, n
         self._h = C.c_void_p()
-        if leaf_rows:
+        if rstack:                  # m = rstack * n rows: a stack of `rstack` upper-triangular factors
+            check(lib().b200qr_tsqr_create_rstack(C.byref(self._h), rstack, n), "b200qr_tsqr_create_rstack")
+        elif leaf_rows:
             check(lib().b200qr_tsqr_create(C.byref(self._h), m, n, leaf_rows, fanin), "b200qr_tsqr_create")
         else:
             check(lib().b200qr_tsqr_create_streaming(C.byref(self._h), m, n, strips), "b200qr_tsqr_create_streaming")
@@ -392,7 +395,7 @@ class TsqrDist:
         self._local = self._top = None
         if local_reduce is None:
             self._local = Tsqr(m_local, n)
-            self._top = Tsqr(world * n, n, strips=1) if world > 1 else None
+            self._top = Tsqr(world * n, n, rstack=world) if world > 1 else None
         self.local_reduce = local_reduce or self._cuda_local
         self.top_reduce = top_reduce or self._cuda_top
 

@@ -235,6 +235,8 @@ __global__ void __launch_bounds__(128) apply_q_kernel(const float *A, int ldm, c
 // of it and prefetches row c + 1 during step c), which leaves shared memory nearly empty and lets TWO CTAs share an
 // SM (128 registers each): two independent chains per SM.
 
+constexpr int TREE_RB = 32;                 // block rows of the reduction levels (divides every n)
+
 struct StripArgs {
     float *A;                               // rows x n, column-major
     long long ldm, rows, rows_per_strip, blocks_per_strip;
@@ -247,7 +249,10 @@ struct StripArgs {
 
 // SRB = rows per block (a thread's block column lives in registers), MINB = CTAs per SM the register budget allows:
 // <48, 2> is the default (117 registers, no spills; 64 rows spill at 128), <32, 3> trades block height for a third chain.
-template <int SRB, int MINB>
+// TRI = the rows are a stack of n x n upper-triangular factors (a reduction level): the strip's first factor IS the
+// initial triangle, and a block that starts at row r of a factor has nothing but zeros in columns < r, whose
+// reflectors are the identity: its steps start at c = r (640 instead of 1024 steps for a pair with 64-row blocks).
+template <int SRB, int MINB, bool TRI>
 __global__ void __launch_bounds__(256, MINB) tsqr_strip_kernel(const StripArgs a)
 {
     __shared__ __align__(16) float xs[2 * SRB];             // two broadcast slots
@@ -259,10 +264,15 @@ __global__ void __launch_bounds__(256, MINB) tsqr_strip_kernel(const StripArgs a
     if (row1 > a.rows) row1 = a.rows;
     float *col = a.A + (size_t)j * a.ldm;
     float *tau_out = a.tau + (size_t)blockIdx.x * a.blocks_per_strip * n;
+    if (TRI) {                                              // thread j: column j of the first factor -> its triangle
+        for (int c = 0; c <= j; ++c) __stcg(Rg + c * n - (c * (c - 1)) / 2 + (j - c), col[row0 + c]);
+    }
 
-    for (long long r0 = row0; r0 < row1; r0 += SRB, tau_out += n) {
+    for (long long r0 = row0 + (TRI ? n : 0); r0 < row1; r0 += SRB, tau_out += n) {
         const int nr = (int)(row1 - r0 < SRB ? row1 - r0 : SRB);     // a multiple of 4
-        float rc_next = __ldcg(Rg + j);                     // R(0, j): this thread's own store of the previous block
+        const int c0 = TRI ? (int)((r0 - row0) % n) : 0;    // first column of this block that is not all zeros
+        float rc_next = 0.f;                                // R(c0, j): this thread's own store of an earlier block
+        if (j >= c0) rc_next = __ldcg(Rg + c0 * n - (c0 * (c0 - 1)) / 2 + (j - c0));
         float b[SRB];
 #pragma unroll
         for (int r = 0; r < SRB; r += 4) {
@@ -281,8 +291,9 @@ __global__ void __launch_bounds__(256, MINB) tsqr_strip_kernel(const StripArgs a
             return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
         };
         float ssq = sumsq();
+        if (TRI) __syncthreads();                           // the broadcast slots of the previous block (c0 may be odd or even)
 #pragma unroll 1
-        for (int c = 0; c < n; ++c) {
+        for (int c = c0; c < n; ++c) {
             float *x = xs + (c & 1) * SRB;
             float *h2 = hs + (c & 1) * 2;
             const int off = c * n - (c * (c - 1)) / 2;
@@ -384,6 +395,10 @@ struct b200qr_tsqr_s {
     int strips = 0, srb = 48;
     long long rows_per_strip = 0, blocks_per_strip = 0;
     float *d_stream_tau = nullptr, *d_rws = nullptr;
+    // the strips' factors are reduced pairwise by the same kernel (TRI): level l holds `count` factors in `stack`
+    struct SLevel { int count; float *stack = nullptr, *tau = nullptr; };
+    std::vector<SLevel> slevels;
+    bool rstack = false;                // b200qr_tsqr_create_rstack: the input IS level 0's stack of factors
     bool streaming = false;
 };
 
@@ -429,6 +444,7 @@ int b200qr_apply_q(const float *dA, int m, int n, int ldm, const float *dTauComp
 
 // ---- TSQR ------------------------------------------------------------------------------------
 static int build_levels(b200qr_tsqr_s *t, long long count);
+static int build_slevels(b200qr_tsqr_s *t, int count, bool borrowed);
 // Level structure: `count` R factors (n x n) are stacked into a (count*n) x n matrix and factored in
 // groups of `fanin` consecutive factors (one batched problem of fanin*n rows each; a shorter last
 // group of >= 2 factors is its own problem, a single left-over factor passes through).  The group
@@ -469,6 +485,40 @@ static int build_levels(b200qr_tsqr_s *t, long long count)
     return B200QR_OK;
 }
 
+// Pairwise reduction levels of the streaming engine: level l holds `count` factors in its stack (level 0's stack is the
+// caller's matrix when `borrowed`).  tau is zeroed once: the steps a triangular block skips keep tau = 0 (H = I).
+static int build_slevels(b200qr_tsqr_s *t, int count, bool borrowed)
+{
+    const int n = t->n;
+    for (; count > 1; count = (count + 1) / 2) {
+        b200qr_tsqr_s::SLevel L;
+        L.count = count;
+        const size_t taufl = (size_t)((count + 1) / 2) * (n / TREE_RB) * n;   // per pair: the second factor's blocks
+        if (!(borrowed && t->slevels.empty()) && cudaMalloc(&L.stack, sizeof(float) * (size_t)count * n * n) != cudaSuccess)
+            return B200QR_ENOMEM;
+        if (cudaMalloc(&L.tau, sizeof(float) * taufl) != cudaSuccess) { cudaFree(L.stack); return B200QR_ENOMEM; }
+        if (cudaMemset(L.tau, 0, sizeof(float) * taufl) != cudaSuccess) { cudaFree(L.stack); cudaFree(L.tau); return B200QR_ECUDA; }
+        t->slevels.push_back(L);
+    }
+    return B200QR_OK;
+}
+
+// Reduction of `count` stacked n x n upper-triangular factors (a (count*n) x n column-major matrix: the exchange step
+// of the multi-GPU TSQR delivers exactly this) to one, by the pairwise levels of the streaming engine.  Factor with
+// b200qr_tsqr_factor(t, dStack, ld >= count*n, dR): the stack is overwritten with the tree's reflectors.
+int b200qr_tsqr_create_rstack(b200qr_tsqr_t *out, int count, int n)
+{
+    if (!out || n <= 0 || n % TB || n > BQ * TB || count < 1) return B200QR_EINVAL;
+    b200qr_tsqr_s *t = new b200qr_tsqr_s;
+    t->m = (long long)count * n; t->n = n; t->leaf_rows = 0; t->fanin = 2; t->streaming = true; t->rstack = true;
+    t->strips = count;
+    auto fail = [&]() { b200qr_tsqr_destroy(t); return B200QR_ENOMEM; };
+    if (cudaMalloc(&t->d_rws, sizeof(float) * (size_t)((count + 1) / 2) * (n * (n + 1) / 2)) != cudaSuccess) return fail();
+    if (build_slevels(t, count, true) != B200QR_OK) return fail();
+    *out = t;
+    return B200QR_OK;
+}
+
 // Streaming engine: `strips` CTAs (<= 0: two per SM, which is what fits) each reduce a contiguous strip of rows to one
 // R factor; the factors are reduced by the leaf-batch tree, four at a time.  m % 32 == 0, n % 32 == 0, n <= 256.
 int b200qr_tsqr_create_streaming(b200qr_tsqr_t *out, long long m, int n, int strips)
@@ -495,7 +545,7 @@ int b200qr_tsqr_create_streaming(b200qr_tsqr_t *out, long long m, int n, int str
     if (cudaMalloc(&t->d_counter, sizeof(int)) != cudaSuccess) return fail();
     if (cudaMalloc(&t->d_stream_tau, sizeof(float) * (size_t)t->strips * t->blocks_per_strip * n) != cudaSuccess) return fail();
     if (cudaMalloc(&t->d_rws, sizeof(float) * (size_t)t->strips * (n * (n + 1) / 2)) != cudaSuccess) return fail();
-    if (build_levels(t, t->strips) != B200QR_OK) return fail();
+    if (build_slevels(t, t->strips, false) != B200QR_OK) return fail();
     *out = t;
     return B200QR_OK;
 }
@@ -506,13 +556,14 @@ int b200qr_tsqr_destroy(b200qr_tsqr_t t)
     cudaFree(t->d_counter); cudaFree(t->d_leaf_tau);
     for (auto &L : t->levels) { cudaFree(L.stack); cudaFree(L.tau); }
     cudaFree(t->d_stream_tau); cudaFree(t->d_rws);
+    for (auto &L : t->slevels) { cudaFree(L.stack); cudaFree(L.tau); }
     delete t;
     return B200QR_OK;
 }
 
 int b200qr_tsqr_stream_block_rows(b200qr_tsqr_t t) { return t && t->streaming ? t->srb : B200QR_EINVAL; }
 
-int b200qr_tsqr_levels(b200qr_tsqr_t t) { return t ? (int)t->levels.size() + (t->streaming ? 1 : 0) : B200QR_EINVAL; }
+int b200qr_tsqr_levels(b200qr_tsqr_t t) { return t ? (t->streaming ? (int)t->slevels.size() + 1 : (int)t->levels.size()) : B200QR_EINVAL; }
 
 // Factor the m x n matrix dA (column-major, ldm) in place (leaf reflectors) and write the n x n
 // upper-triangular R (column-major, leading dimension n) to dR.  Asynchronous on `stream`.
@@ -527,18 +578,36 @@ int b200qr_tsqr_factor(b200qr_tsqr_t t, float *dA, long long ldm, float *dR, voi
     int src_ld = (int)ldm;
     bool first_stack_filled = false;
     if (t->streaming) {
-        CKB(cudaMemsetAsync(t->d_rws, 0, sizeof(float) * (size_t)t->strips * (n * (n + 1) / 2), stream));
         StripArgs a;
-        a.A = dA; a.ldm = ldm; a.rows = t->m; a.rows_per_strip = t->rows_per_strip; a.blocks_per_strip = t->blocks_per_strip;
-        a.n = n; a.tau = t->d_stream_tau; a.Rws = t->d_rws;
-        a.Rout = t->strips > 1 ? t->levels[0].stack : dR;             // the strips' triangles ARE the first level's stack
-        a.ldr = t->strips > 1 ? (long long)t->strips * n : n;
-        if (t->srb == 32) tsqr_strip_kernel<32, 3><<<t->strips, n, 0, stream>>>(a);
-        else if (t->srb == 64) tsqr_strip_kernel<64, 2><<<t->strips, n, 0, stream>>>(a);
-        else tsqr_strip_kernel<48, 2><<<t->strips, n, 0, stream>>>(a);
-        CKB(cudaGetLastError());
-        if (t->strips == 1) return B200QR_OK;
-        first_stack_filled = true;
+        a.n = n; a.Rws = t->d_rws;
+        if (!t->rstack) {
+            CKB(cudaMemsetAsync(t->d_rws, 0, sizeof(float) * (size_t)t->strips * (n * (n + 1) / 2), stream));
+            a.A = dA; a.ldm = ldm; a.rows = t->m; a.rows_per_strip = t->rows_per_strip; a.blocks_per_strip = t->blocks_per_strip;
+            a.tau = t->d_stream_tau;
+            a.Rout = t->strips > 1 ? t->slevels[0].stack : dR;        // the strips' triangles ARE the first level's stack
+            a.ldr = t->strips > 1 ? (long long)t->strips * n : n;
+            if (t->srb == 32) tsqr_strip_kernel<32, 3, false><<<t->strips, n, 0, stream>>>(a);
+            else if (t->srb == 64) tsqr_strip_kernel<64, 2, false><<<t->strips, n, 0, stream>>>(a);
+            else tsqr_strip_kernel<48, 2, false><<<t->strips, n, 0, stream>>>(a);
+            CKB(cudaGetLastError());
+        } else if (t->strips == 1) {                                  // a stack of one factor: R is that factor
+            gather_r_kernel<<<64, 256, 0, stream>>>(dA, 0, (int)ldm, n, 1, dR);
+            CKB(cudaGetLastError());
+        }
+        // pairwise reduction of the stacked factors: level l's strips write level l + 1's stack, the last one dR
+        for (size_t l = 0; l < t->slevels.size(); ++l) {
+            auto &L = t->slevels[l];
+            const int pairs = (L.count + 1) / 2;
+            const bool borrowed = t->rstack && l == 0;
+            a.A = borrowed ? dA : L.stack; a.ldm = borrowed ? ldm : (long long)L.count * n; a.rows = (long long)L.count * n;
+            a.rows_per_strip = 2 * n; a.blocks_per_strip = n / TREE_RB;
+            a.tau = L.tau;                                           // a.Rws: the first `pairs` triangles are reused
+            a.Rout = pairs > 1 ? t->slevels[l + 1].stack : dR;
+            a.ldr = pairs > 1 ? (long long)pairs * n : n;
+            tsqr_strip_kernel<TREE_RB, 3, true><<<pairs, n, 0, stream>>>(a);
+            CKB(cudaGetLastError());
+        }
+        return B200QR_OK;
     } else {
         long long count = t->m / t->leaf_rows;
         rc = batched_launch(dA, t->leaf_rows, n, (int)ldm, t->leaf_rows, (int)count, t->d_leaf_tau, t->d_counter, stream);

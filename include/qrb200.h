@@ -172,6 +172,10 @@ int b200qr_tsqr_create(b200qr_tsqr_t *t, long long m, int n, int leaf_rows, int 
  * rows x n per TSQRT step, strips of ceil(m / strips) rows rounded up to whole blocks) and in the plan (tree). */
 int b200qr_tsqr_create_streaming(b200qr_tsqr_t *t, long long m, int n, int strips);
 int b200qr_tsqr_stream_block_rows(b200qr_tsqr_t t);
+/* Reduction of `count` stacked n x n upper-triangular factors ((count*n) x n, column-major) to one by the streaming
+ * engine's pairwise levels: the top of the multi-GPU TSQR (all-gather of the ranks' R factors, then every
+ * rank reduces the stack).  b200qr_tsqr_factor(t, dStack, ld, dR) overwrites the stack with the tree's reflectors. */
+int b200qr_tsqr_create_rstack(b200qr_tsqr_t *t, int count, int n);
 int b200qr_tsqr_destroy(b200qr_tsqr_t t);
 int b200qr_tsqr_levels(b200qr_tsqr_t t);
 int b200qr_tsqr_factor(b200qr_tsqr_t t, float *dA, long long ldm, float *dR, void *stream);

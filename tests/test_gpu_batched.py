@@ -146,3 +146,27 @@ def test_tsqr_streaming_reflectors_reproduce_r(cuda, qr):
     scale = top.abs().max().item()
     assert bot.abs().max().item() <= 2e-5 * scale        # everything below the triangle is annihilated
     assert (top - R.t().double()).abs().max().item() <= 2e-5 * scale
+
+
+@pytest.mark.parametrize("count,n", [(1, 64), (2, 256), (5, 128), (8, 256), (13, 32)])
+def test_tsqr_rstack_reduction(cuda, qr, count, n):
+    """Pairwise reduction of stacked upper-triangular factors (the top of the multi-GPU TSQR): R^T R = sum_i R_i^T R_i and
+    R equals LAPACK's R of the stack up to row signs; the identity steps of the triangular blocks leave tau = 0."""
+    torch = cuda
+    g = torch.Generator(device="cuda").manual_seed(31 + count)
+    blocks = torch.triu(torch.rand((count, n, n), generator=g, device="cuda", dtype=torch.float32) * 2 - 1)   # [i, row, col]
+    stack = blocks.reshape(count * n, n).t().contiguous()            # column-major (count*n) x n: [col, row]
+    ref = stack.clone()
+    t = qr.Tsqr(count * n, n, rstack=count)
+    R = torch.full((n, n), 3.0, device="cuda")
+    t.factor(stack.data_ptr(), count * n, R.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    t.close()
+    Rm = R.t().double()
+    assert torch.count_nonzero(torch.tril(Rm, -1)) == 0
+    S = ref.t().double()
+    G = S.t() @ S
+    assert (torch.linalg.norm(Rm.t() @ Rm - G) / torch.linalg.norm(G)).item() <= 50 * float(np.finfo(np.float32).eps)
+    R64 = torch.linalg.qr(S, mode="r").R
+    sg = torch.sign(torch.diagonal(R64)) * torch.sign(torch.diagonal(Rm))
+    assert (torch.max(torch.abs(Rm - sg[:, None] * R64)) / torch.max(torch.abs(R64))).item() <= 1e-4
