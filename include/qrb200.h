@@ -161,8 +161,8 @@ int b200qr_batched_last_cuda_error(void);
  * one n x n R is left.  The reference handles a tall panel as one serial TSQRT chain
  * (gridscheduler.c:136-154); the tree changes the Householder-vector layout (leaf reflectors stay in
  * dA, inner nodes in the plan), so parity for this path is on R up to row signs.  For several
- * GPUs: one plan per row block, all-gather the R factors, stack them and call
- * b200qr_batched_factor once more (see bench.py / tests).                                       */
+ * GPUs: one plan per row block, all-gather the R factors (NCCL), reduce the stack on every rank with
+ * b200qr_tsqr_create_rstack (host side: TsqrDist in the Python package, tools/bench_tsqr_dist.py). */
 typedef struct b200qr_tsqr_s *b200qr_tsqr_t;
 int b200qr_tsqr_create(b200qr_tsqr_t *t, long long m, int n, int leaf_rows, int fanin);
 /* Streaming engine for the same job (same b200qr_tsqr_factor / _destroy): `strips` CTAs (<= 0: two per SM) each walk a
