@@ -98,9 +98,10 @@ if __name__ == "__main__":
         for leaf in (512, 2048):
             tsqr(leaf=leaf)
     if which in ("all", "tsqr", "stream"):
-        for rb in ("48", "32", "64"):                 # block rows / CTAs per SM: <48, 2> (default), <32, 3>, <64, 2>
-            os.environ["QRB200_TSQR_RB"] = rb
-            print("QRB200_TSQR_RB=" + rb, end="  ")
+        for nb, rb in (("8", "48"), ("8", "32"), ("1", "48")):   # reflectors per barrier x block rows
+            os.environ["QRB200_TSQR_NB"], os.environ["QRB200_TSQR_RB"] = nb, rb
+            print("QRB200_TSQR_NB=%s QRB200_TSQR_RB=%s" % (nb, rb), end="  ")
             tsqr_streaming(strips=0)
         os.environ.pop("QRB200_TSQR_RB", None)
+        os.environ.pop("QRB200_TSQR_NB", None)
         tsqr_streaming(m=1048576)
