@@ -1536,7 +1536,12 @@ void cudaQRTask(float *mat, int m, int n, int ldm, int maxblocks)
         const char *ov = getenv("QRB200_OVERLAP");
         const int nc = g_cache.plan->nc;
         const bool able = nc == 1 || nc == 2 || nc == 5;               // engines that publish "tile column final"
-        const bool want = ov && *ov ? atoi(ov) != 0 : (sizeof(float) * (size_t)m * n >= ((size_t)32 << 20) && host_pinned(mat));
+        // A profiler that serialises kernels (ncu replays each launch with the host held back) can never deliver the
+        // input to a kernel that is already running: under an injection library the copies stay serial unless forced.
+        const bool profiled = getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") ||
+                              getenv("NV_NSIGHT_INJECTION_TRANSPORT_TYPE");
+        const bool want = ov && *ov ? atoi(ov) != 0
+                                    : (!profiled && sizeof(float) * (size_t)m * n >= ((size_t)32 << 20) && host_pinned(mat));
         if (able && want) {
             const int orc = legacy_overlapped(mat, m, n, ldm, quiet);
             if (orc <= 0) {

@@ -14,9 +14,9 @@ pytestmark = pytest.mark.gpu
 
 
 def run_legacy(L, host_ptr, m, n, ldm, env):
+    env = dict(env, QRB200_QUIET="1")                 # restored below: later tests check the legacy prints
     old = {k: os.environ.get(k) for k in env}
     os.environ.update(env)
-    os.environ["QRB200_QUIET"] = "1"
     try:
         L.cudaQRTask(C.c_void_p(host_ptr), m, n, ldm, 128)
     finally:
