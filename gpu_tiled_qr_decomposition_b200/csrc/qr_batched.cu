@@ -350,6 +350,119 @@ __global__ void __launch_bounds__(256, MINB) tsqr_strip_kernel(const StripArgs a
 }
 
 
+// Same kernel with a shorter per-reflector chain: the next owner broadcasts its column the moment it is updated
+// (before its sum of squares, rsqrt and reciprocal), and the step has two barriers -- (A) column visible, (B) Householder
+// scalars visible -- so every other warp's dot product with the new column overlaps the owner's scalar work.
+// MEASURED (B200, 4 194 304 x 256): 56.9 ms (48-row blocks) / 51.7 ms (32-row blocks, 3 CTAs per SM) against 48.0 ms for
+// the one-barrier kernel -- same numbers bit for bit, but the second barrier costs more than the overlap returns: with
+// two or three CTAs per SM the other CTAs already fill the owner's scalar work.  Kept behind QRB200_TSQR_EARLY=1.
+template <int SRB, int MINB, bool TRI>
+__global__ void __launch_bounds__(256, MINB) tsqr_strip_early_kernel(const StripArgs a)
+{
+    __shared__ __align__(16) float xs[2 * SRB];             // two broadcast slots
+    __shared__ float hs[4];                                 // two slots of {1/piv, tau}
+    const int n = a.n, j = threadIdx.x;
+    float *Rg = a.Rws + (size_t)blockIdx.x * (n * (n + 1) / 2);    // (c, col) at c*n - c*(c-1)/2 + (col - c)
+    const long long row0 = (long long)blockIdx.x * a.rows_per_strip;
+    long long row1 = row0 + a.rows_per_strip;
+    if (row1 > a.rows) row1 = a.rows;
+    float *col = a.A + (size_t)j * a.ldm;
+    float *tau_out = a.tau + (size_t)blockIdx.x * a.blocks_per_strip * n;
+    if (TRI) {                                              // thread j: column j of the first factor -> its triangle
+        for (int c = 0; c <= j; ++c) __stcg(Rg + c * n - (c * (c - 1)) / 2 + (j - c), col[row0 + c]);
+    }
+
+    for (long long r0 = row0 + (TRI ? n : 0); r0 < row1; r0 += SRB, tau_out += n) {
+        const int nr = (int)(row1 - r0 < SRB ? row1 - r0 : SRB);     // a multiple of 4
+        const int c0 = TRI ? (int)((r0 - row0) % n) : 0;    // first column of this block that is not all zeros
+        float rc_next = 0.f;                                // R(c0, j): this thread's own store of an earlier block
+        if (j >= c0) rc_next = __ldcg(Rg + c0 * n - (c0 * (c0 - 1)) / 2 + (j - c0));
+        float b[SRB];
+#pragma unroll
+        for (int r = 0; r < SRB; r += 4) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nr) v = __ldcs(reinterpret_cast<const float4 *>(col + r0 + r));
+            b[r] = v.x; b[r + 1] = v.y; b[r + 2] = v.z; b[r + 3] = v.w;
+        }
+        auto sumsq = [&]() {
+            float s[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[i] = b[i] * b[i];
+#pragma unroll
+            for (int r = 8; r < SRB; r += 8)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s[i] = fmaf(b[r + i], b[r + i], s[i]);
+            return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+        };
+        if (j == c0) {                                      // the block's first owner broadcasts its column right away
+            float *x0 = xs + (c0 & 1) * SRB;
+#pragma unroll
+            for (int r = 0; r < SRB; r += 4) *reinterpret_cast<float4 *>(x0 + r) = make_float4(b[r], b[r + 1], b[r + 2], b[r + 3]);
+        }
+#pragma unroll 1
+        for (int c = c0; c < n; ++c) {
+            float *x = xs + (c & 1) * SRB;
+            float *h2 = hs + (c & 1) * 2;
+            const int off = c * n - (c * (c - 1)) / 2;
+            const float rc = rc_next;                       // R(c, j), valid for j >= c
+            if (j > c) rc_next = __ldcg(Rg + off + (n - c) + (j - c - 1));     // R(c + 1, j): in flight during this step
+            __syncthreads();                                // (A) x_c is visible
+            if (j == c) {                                   // owner: Householder scalars, while the others do their dot products
+                const HouseScalars h = house_scalars(rc, sumsq());
+                h2[0] = h.inv; h2[1] = h.tau;
+                tau_out[c] = h.tau;
+            }
+            float d = 0.f;
+            if (j >= c) {
+                float s[8];
+#pragma unroll
+                for (int i = 0; i < 8; i += 4) {
+                    const float4 xv = *reinterpret_cast<const float4 *>(x + i);
+                    s[i] = b[i] * xv.x; s[i + 1] = b[i + 1] * xv.y; s[i + 2] = b[i + 2] * xv.z; s[i + 3] = b[i + 3] * xv.w;
+                }
+#pragma unroll
+                for (int r = 8; r < SRB; r += 8)
+#pragma unroll
+                    for (int i = 0; i < 8; i += 4) {
+                        const float4 xv = *reinterpret_cast<const float4 *>(x + r + i);
+                        s[i] = fmaf(b[r + i], xv.x, s[i]); s[i + 1] = fmaf(b[r + i + 1], xv.y, s[i + 1]);
+                        s[i + 2] = fmaf(b[r + i + 2], xv.z, s[i + 2]); s[i + 3] = fmaf(b[r + i + 3], xv.w, s[i + 3]);
+                    }
+                d = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+            }
+            __syncthreads();                                // (B) (1/piv, tau) of reflector c are visible
+            const float inv = h2[0], tau = h2[1];
+            // the reflector replaces column c of the block
+            {
+                float *vcol = a.A + (size_t)c * a.ldm + r0;
+                for (int t = j; t < nr; t += n) vcol[t] = x[t] * inv;
+            }
+            if (j >= c) {
+                // beta = tau (R(c,j) + v' B(:,j)),  v = x / piv
+                const float beta = tau * fmaf(inv, d, rc);
+                __stcg(Rg + off + j - c, rc - beta);
+                if (j > c) {
+                    const float g = -beta * inv;
+#pragma unroll
+                    for (int r = 0; r < SRB; r += 4) {
+                        const float4 xv = *reinterpret_cast<const float4 *>(x + r);
+                        b[r] = fmaf(g, xv.x, b[r]); b[r + 1] = fmaf(g, xv.y, b[r + 1]);
+                        b[r + 2] = fmaf(g, xv.z, b[r + 2]); b[r + 3] = fmaf(g, xv.w, b[r + 3]);
+                    }
+                    if (j == c + 1) {                       // the next owner broadcasts its column at once: the other warps'
+                        float *xn = xs + ((c + 1) & 1) * SRB;       // dot products then overlap its sum of squares / rsqrt / rcp
+#pragma unroll
+                        for (int r = 0; r < SRB; r += 4) *reinterpret_cast<float4 *>(xn + r) = make_float4(b[r], b[r + 1], b[r + 2], b[r + 3]);
+                    }
+                }
+            }
+        }
+    }
+    float *rcol = a.Rout + (size_t)j * a.ldr + (size_t)blockIdx.x * n;
+    for (int c = 0; c < n; ++c) rcol[c] = (c <= j) ? __ldcg(Rg + c * n - (c * (c - 1)) / 2 + (j - c)) : 0.f;
+}
+
+
 // ---- the same recurrence, WNB reflectors per barrier (compact-WY inside the block) -----------------------------------
 // The one-reflector-per-barrier kernel above keeps all eight warps on the per-reflector chain.  Here the warp that owns
 // the next WNB columns factors them by itself (phase A: the same steps, but __syncwarp instead of a CTA barrier, and
@@ -596,6 +709,7 @@ struct b200qr_tsqr_s {
     struct SLevel { int count; float *stack = nullptr, *tau = nullptr; };
     std::vector<SLevel> slevels;
     bool rstack = false;                // b200qr_tsqr_create_rstack: the input IS level 0's stack of factors
+    bool early = false;                 // QRB200_TSQR_EARLY=1: two-barrier variant (measured slower, see tsqr_strip_early_kernel)
     bool wy = false;                    // QRB200_TSQR_NB=8: WNB reflectors per barrier (measured slower, see tsqr_strip_wy_kernel)
     bool streaming = false;
 };
@@ -711,6 +825,7 @@ int b200qr_tsqr_create_rstack(b200qr_tsqr_t *out, int count, int n)
     t->m = (long long)count * n; t->n = n; t->leaf_rows = 0; t->fanin = 2; t->streaming = true; t->rstack = true;
     t->strips = count;
     if (const char *e = getenv("QRB200_TSQR_NB")) t->wy = atoi(e) == WNB;
+    if (const char *e = getenv("QRB200_TSQR_EARLY")) t->early = atoi(e) != 0;
     auto fail = [&]() { b200qr_tsqr_destroy(t); return B200QR_ENOMEM; };
     if (cudaMalloc(&t->d_rws, sizeof(float) * (size_t)((count + 1) / 2) * (n * (n + 1) / 2)) != cudaSuccess) return fail();
     if (build_slevels(t, count, true) != B200QR_OK) return fail();
@@ -735,7 +850,8 @@ int b200qr_tsqr_create_streaming(b200qr_tsqr_t *out, long long m, int n, int str
     auto fail = [&]() { b200qr_tsqr_destroy(t); return B200QR_ENOMEM; };
     if (const char *e = getenv("QRB200_TSQR_RB")) { const int v = atoi(e); if (v == 32 || v == 48 || v == 64) t->srb = v; }
     if (const char *e = getenv("QRB200_TSQR_NB")) t->wy = atoi(e) == WNB;
-    if (t->wy && t->srb == 64) t->srb = 48;
+    if (const char *e = getenv("QRB200_TSQR_EARLY")) t->early = atoi(e) != 0;
+    if ((t->wy || t->early) && t->srb == 64) t->srb = 48;
     const int SRB = t->srb;
     if (strips_auto) strips = sms * (SRB == 32 && !t->wy ? 3 : 2);
     long long rps = (m + strips - 1) / strips;
@@ -790,6 +906,9 @@ int b200qr_tsqr_factor(b200qr_tsqr_t t, float *dA, long long ldm, float *dR, voi
             if (t->wy) {
                 if (t->srb == 32) tsqr_strip_wy_kernel<32, 2, false><<<t->strips, n, 0, stream>>>(a);
                 else tsqr_strip_wy_kernel<48, 2, false><<<t->strips, n, 0, stream>>>(a);
+            } else if (t->early) {
+                if (t->srb == 32) tsqr_strip_early_kernel<32, 3, false><<<t->strips, n, 0, stream>>>(a);
+                else tsqr_strip_early_kernel<48, 2, false><<<t->strips, n, 0, stream>>>(a);
             } else if (t->srb == 32) tsqr_strip_kernel<32, 3, false><<<t->strips, n, 0, stream>>>(a);
             else if (t->srb == 64) tsqr_strip_kernel<64, 2, false><<<t->strips, n, 0, stream>>>(a);
             else tsqr_strip_kernel<48, 2, false><<<t->strips, n, 0, stream>>>(a);
@@ -809,6 +928,7 @@ int b200qr_tsqr_factor(b200qr_tsqr_t t, float *dA, long long ldm, float *dR, voi
             a.Rout = pairs > 1 ? t->slevels[l + 1].stack : dR;
             a.ldr = pairs > 1 ? (long long)pairs * n : n;
             if (t->wy) tsqr_strip_wy_kernel<TREE_RB, 2, true><<<pairs, n, 0, stream>>>(a);
+            else if (t->early) tsqr_strip_early_kernel<TREE_RB, 3, true><<<pairs, n, 0, stream>>>(a);
             else tsqr_strip_kernel<TREE_RB, 3, true><<<pairs, n, 0, stream>>>(a);
             CKB(cudaGetLastError());
         }

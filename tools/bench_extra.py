@@ -98,10 +98,11 @@ if __name__ == "__main__":
         for leaf in (512, 2048):
             tsqr(leaf=leaf)
     if which in ("all", "tsqr", "stream"):
-        for nb, rb in (("8", "48"), ("8", "32"), ("1", "48")):   # reflectors per barrier x block rows
-            os.environ["QRB200_TSQR_NB"], os.environ["QRB200_TSQR_RB"] = nb, rb
-            print("QRB200_TSQR_NB=%s QRB200_TSQR_RB=%s" % (nb, rb), end="  ")
+        for early, nb, rb in (("1", "1", "48"), ("1", "1", "32"), ("0", "1", "48"), ("0", "8", "48")):
+            # early broadcast of the next column (two barriers) / reflectors per barrier / block rows
+            os.environ["QRB200_TSQR_EARLY"], os.environ["QRB200_TSQR_NB"], os.environ["QRB200_TSQR_RB"] = early, nb, rb
+            print("QRB200_TSQR_EARLY=%s QRB200_TSQR_NB=%s QRB200_TSQR_RB=%s" % (early, nb, rb), end="  ")
             tsqr_streaming(strips=0)
-        os.environ.pop("QRB200_TSQR_RB", None)
-        os.environ.pop("QRB200_TSQR_NB", None)
+        for k in ("QRB200_TSQR_EARLY", "QRB200_TSQR_NB", "QRB200_TSQR_RB"):
+            os.environ.pop(k, None)
         tsqr_streaming(m=1048576)
