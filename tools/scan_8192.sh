@@ -1,11 +1,19 @@
 #!/bin/bash
-# A/B scan of the panel-CTA count and the sweep-ticket lag at 8192^2 (both engines); prints one line per configuration.
+# A/B scan at 8192^2: panel-CTA count (QRB200_NP) x sweep-ticket lag (QRB200_LAG) for the tensor-core engine, panel-CTA
+# count for the SIMT engine.  One line per configuration ("-" = the plan's default).  ~5 s of process start-up per line.
 cd "$(dirname "$0")/.."
-for np in "" 4 8 12 16 24; do
-  for lag in "" 4 8 32; do
-    QRB200_NP=$np QRB200_LAG=$lag python tools/tc3_time.py 8192 3 2>&1 | tail -1 | sed "s/$/ lag=${lag:--}/"
+run() { env "$@" python tools/tc3_time.py 8192 "$TC" 2>&1 | tail -1 | sed "s/\$/  [$*]/"; }
+TC=3
+for np in - 4 16; do
+  for lag in - 0 4 8 32; do
+    args=()
+    [ "$np" != - ] && args+=("QRB200_NP=$np")
+    [ "$lag" != - ] && args+=("QRB200_LAG=$lag")
+    run "${args[@]}" X=1
   done
 done
-for np in "" 8 12 16 24 32; do
-  QRB200_NP=$np python tools/tc3_time.py 8192 0 2>&1 | tail -1
+TC=0
+for np in - 8 16 32; do
+  args=(); [ "$np" != - ] && args+=("QRB200_NP=$np")
+  run "${args[@]}" X=1
 done
