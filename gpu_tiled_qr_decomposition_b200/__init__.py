@@ -23,7 +23,7 @@ EXPORTS = (
     "b200qr_plan_macro_tasks", "b200qr_factor_device", "b200qr_plan_tau_device",
     "b200qr_tau_to_reference", "b200qr_factor_host", "b200qr_plan_read_trace", "b200qr_tile_task",
     "b200qr_sched_init", "b200qr_sched_next", "b200qr_sched_done", "b200qr_sched_free",
-    "b200qr_sched_progress", "b200qr_sched_ready_count", "b200qr_sched_dep_count",
+    "b200qr_sched_progress", "b200qr_sched_final_progress", "b200qr_sched_ready_count", "b200qr_sched_dep_count",
     "b200qr_sched_predecessors", "b200qr_sched_device_order", "b200qr_sched_sweep_order", "b200qr_sched_rank_tickets", "b200qr_sched_sweep_order_skew",
     "b200qr_sched_rank_tickets_skew", "b200qr_sched_sweep_order_lag",
     "b200qr_dist_create", "b200qr_dist_destroy", "b200qr_dist_handle_bytes", "b200qr_dist_export",

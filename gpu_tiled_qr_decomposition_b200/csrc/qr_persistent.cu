@@ -1402,13 +1402,10 @@ static bool host_pinned(const void *ptr)
     return a.type == cudaMemoryTypeHost;
 }
 
-static bool column_final(const int *w, int j, int p, int K)
+static bool column_final(const int *w, int j, int p, int q)
 {
-    for (int i = 0; i < p; ++i) {
-        const int lo = i < j ? i : j;
-        const int want = (i == j && j < K) ? j + 2 : (lo + 1 < K ? lo + 1 : K);
-        if (w[i] != want) return false;
-    }
+    for (int i = 0; i < p; ++i)
+        if (w[i] != b200qr_sched_final_progress(p, q, i, j)) return false;
     return true;
 }
 
@@ -1417,7 +1414,7 @@ static int legacy_overlapped(float *mat, int m, int n, int ldm, bool quiet)
 {
     LegacyCache &c = g_cache;
     b200qr_plan_s *pl = c.plan;
-    const int p = pl->p, q = pl->q, K = pl->K;
+    const int p = pl->p, q = pl->q;
     if (!c.ks) {
         bool ok = cudaStreamCreateWithFlags(&c.ks, cudaStreamNonBlocking) == cudaSuccess &&
                   cudaStreamCreateWithFlags(&c.hs, cudaStreamNonBlocking) == cudaSuccess &&
@@ -1473,7 +1470,7 @@ static int legacy_overlapped(float *mat, int m, int n, int ldm, bool quiet)
                "polling");
             ck(cudaStreamSynchronize(c.ps), "polling");
             int adv = 0;
-            while (adv < w && column_final(c.h_prog + (size_t)adv * p, jready + adv, p, K)) ++adv;
+            while (adv < w && column_final(c.h_prog + (size_t)adv * p, jready + adv, p, q)) ++adv;
             jready += adv;
         }
         if (jready - jdone >= ct || (jready == q && jready > jdone)) { copy_back(jdone, jready); jdone = jready; }

@@ -102,6 +102,18 @@ void b200qr_sched_done(b200qr_sched_t s, const b200qr_task *t)
 int b200qr_sched_progress(b200qr_sched_t s, int l, int m) { return s->inside(l, m) ? s->P(l, m) : -1; }
 int b200qr_sched_ready_count(b200qr_sched_t s) { return s->ready; }
 
+// Value of the device's progress word of tile (l, m) once its tile column is final: the number of steps the tile takes
+// part in, min(l, m) + 1 capped at K = min(p, q) -- what b200qr_sched_progress() reads when the DAG has run dry -- plus
+// one on the diagonal, where the panel's last store publishes "column final" (run_panel in qr_persistent.cu).  The
+// overlapped host path of cudaQRTask compares the words it polls with this.
+int b200qr_sched_final_progress(int p, int q, int l, int m)
+{
+    if (p <= 0 || q <= 0 || l < 0 || m < 0 || l >= p || m >= q) return -1;
+    const int K = p < q ? p : q, lo = l < m ? l : m;
+    const int steps = lo + 1 < K ? lo + 1 : K;
+    return steps + ((l == m && m < K) ? 1 : 0);
+}
+
 int b200qr_sched_dep_count(int type, int k)
 {
     int prev = k > 0 ? 1 : 0;            // DAPP(l,m,k-1) on the same tile

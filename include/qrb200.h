@@ -213,6 +213,7 @@ int  b200qr_sched_next(b200qr_sched_t s, b200qr_task *out);        /* getNextTas
 void b200qr_sched_done(b200qr_sched_t s, const b200qr_task *t);    /* doneATask      */
 void b200qr_sched_free(b200qr_sched_t s);
 int  b200qr_sched_progress(b200qr_sched_t s, int l, int m);        /* prog[l][m]     */
+int  b200qr_sched_final_progress(int p, int q, int l, int m);       /* device word of a finished tile column (diagonal: +1) */
 int  b200qr_sched_ready_count(b200qr_sched_t s);
 int  b200qr_sched_dep_count(int type, int k);   /* initial dependency counter of a task */
 /* Predecessors of task t (at most 3); returns how many were written to pred[].      */

@@ -200,3 +200,23 @@ def test_lagged_sweep_order_is_topological(qr):
                 assert pos[(k - 1, g)] < i
             if k >= 1 and (k - 1, k // G) in pos:                  # diagonal group of step k-1 holds tile column k
                 assert pos[(k - 1, k // G)] < i
+
+
+def test_final_progress_words_match_the_host_mirror(qr):
+    """The words the overlapped cudaQRTask path waits for (b200qr_sched_final_progress) are the host mirror's progress
+    words once the DAG has run dry, plus the panel's "column final" publish on the diagonal."""
+    import ctypes as C
+    L = qr.lib()
+    T = qr.Task
+    for (p, q) in [(1, 1), (4, 4), (7, 3), (3, 7), (16, 4), (9, 9)]:
+        s = L.b200qr_sched_init(p, q)
+        t = T()
+        while L.b200qr_sched_next(s, C.byref(t)) == qr.TASK_AVAIL:
+            L.b200qr_sched_done(s, C.byref(t))
+        K = min(p, q)
+        for l in range(p):
+            for m in range(q):
+                want = L.b200qr_sched_progress(s, l, m) + (1 if (l == m and m < K) else 0)
+                assert L.b200qr_sched_final_progress(p, q, l, m) == want, (p, q, l, m)
+        L.b200qr_sched_free(s)
+        assert L.b200qr_sched_final_progress(p, q, p, 0) == -1 and L.b200qr_sched_final_progress(p, q, 0, -1) == -1
