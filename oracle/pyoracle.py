@@ -108,6 +108,32 @@ def tiled_qr(a, m, n, b=32, ldm=None, order="static"):
     return out, tau
 
 
+def tsqr_stream(a, m, n, block_rows):
+    """Tall-skinny QR by ONE TSQRT chain whose tile is as wide as the matrix -- the recurrence the streaming engine of
+    the product runs per strip: R starts as the empty n x n triangle and every block of `block_rows` rows is one call of
+    the TSQRT restatement (oracle_tsqrt = qrdecomp.c:689-721 STSQRF + 1243-1272 calcvkDouble + 647-687 updateDoubleQ_WY,
+    whose tile sizes are parameters) with ma = n, mb = block_rows.  `a`: (n, m) float32 storage of the column-major m x n
+    matrix.  Returns (V, tau, R): V (n, m) storage with every block replaced by its reflector block V2, tau
+    (m / block_rows, n), R (n, n) storage, upper triangular ([column, row])."""
+    assert m % block_rows == 0
+    L = lib()
+    V = np.ascontiguousarray(a, dtype=np.float32).copy()
+    nblk = m // block_rows
+    tau = np.zeros((nblk, n), dtype=np.float32)
+    ld = n + block_rows
+    buf = np.zeros((n, ld), dtype=np.float32)                # [R ; block], one leading dimension for both (oracle_tsqrt)
+    work = np.zeros(ld + 8, dtype=np.float32)
+    for bi in range(nblk):
+        rows = slice(bi * block_rows, (bi + 1) * block_rows)
+        buf[:, n:] = V[:, rows]
+        t = np.zeros(n, dtype=np.float32)
+        top = buf.reshape(-1)
+        L.oracle_tsqrt(top, top[n:], t, n, block_rows, n, ld, work)
+        V[:, rows] = buf[:, n:]
+        tau[bi] = t
+    return V, tau, np.ascontiguousarray(buf[:, :n])
+
+
 def ref_tiled_qr(a, m, n, ldm=None, fast=False):
     """The reference's own taskQRP_threads (8 pthreads, b = 32)."""
     ldm = ldm or m

@@ -103,3 +103,30 @@ def test_oracle_quality(po):
         assert back < 1.0 and orth < 3.0
         tau2 = po.tau_from_v(out, m, n, 32)
         assert np.max(np.abs(tau2 - tau)) < 2e-6
+
+
+@pytest.mark.parametrize("m,n,rb", [(1536, 64, 48), (512, 128, 32), (768, 32, 48), (256, 256, 64)])
+def test_streaming_tsqr_oracle(po, m, n, rb):
+    """The TSQRT restatement with an n-wide tile, chained over blocks of rows from an empty triangle (what the product's
+    streaming TSQR engine runs per strip): R equals float64 LAPACK's up to row signs, and the reflector blocks it leaves
+    behind reproduce [R; 0] when replayed on [0; A] in float64 with tau from the oracle."""
+    rng = np.random.default_rng(m + n)
+    a = rng.uniform(-1, 1, (n, m)).astype(np.float32)
+    V, tau, R = po.tsqr_stream(a, m, n, rb)
+    Rm = R.T.astype(np.float64)
+    assert np.count_nonzero(np.tril(Rm, -1)) == 0
+    R64 = np.linalg.qr(a.T.astype(np.float64), mode="r")
+    sg = np.sign(np.diag(R64)) * np.sign(np.diag(Rm))
+    assert np.max(np.abs(Rm - sg[:, None] * R64)) <= 1e-4 * np.max(np.abs(R64))
+    top = np.zeros((n, n))
+    bot = a.T.astype(np.float64).copy()
+    Vd = V.T.astype(np.float64)
+    for bi in range(m // rb):
+        rows = slice(bi * rb, (bi + 1) * rb)
+        for c in range(n):
+            v2 = Vd[rows, c]
+            w = float(tau[bi, c]) * (top[c, :] + v2 @ bot[rows, :])
+            top[c, :] -= w
+            bot[rows, :] -= np.outer(v2, w)
+    scale = np.max(np.abs(top))
+    assert np.max(np.abs(bot)) <= 2e-5 * scale and np.max(np.abs(top - Rm)) <= 2e-5 * scale
