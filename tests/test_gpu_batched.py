@@ -176,7 +176,11 @@ def test_tsqr_rstack_reduction(cuda, qr, count, n):
 def test_tsqr_streaming_matches_oracle_elementwise(cuda, qr, po, m, n):
     """One strip of the streaming engine against the oracle's chain of n-wide TSQRT steps (pyoracle.tsqr_stream = the
     reference's STSQRF restated, qrdecomp.c:689-721) on the same input and block height: R and every reflector block
-    agree element by element (float32 rounding only: FMA, split sums, tau = 1 + |x0| / nrm vs 2 / (1 + |v|^2))."""
+    agree element by element (float32 rounding only: FMA, split sums, tau = 1 + |x0| / nrm vs 2 / (1 + |v|^2)).
+    Only shapes whose rank-deficient start-up phase is short are comparable this way: at n = 256 (six 48-row blocks
+    before the triangle has full rank) the pivots of the undetermined columns are rounding noise whose signs decide the
+    final row signs, and even two float32 CPU implementations part ways (profiles/r1_measurements.md); there the
+    criterion is R up to row signs (test_tsqr_streaming_r_factor)."""
     torch = cuda
     rng = np.random.default_rng(5 * m + n)
     a = rng.uniform(-1, 1, (n, m)).astype(np.float32)
