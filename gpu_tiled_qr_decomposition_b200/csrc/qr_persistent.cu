@@ -1441,6 +1441,8 @@ static int legacy_overlapped(float *mat, int m, int n, int ldm, bool quiet)
     if (rc != B200QR_OK) { printf("error running QR kernel: %s\n", b200qr_strerror(rc)); cudaStreamSynchronize(c.ks); return -1; }
     // ---- in: chunks of tile columns, each followed by zeros onto its progress words
     ck(cudaStreamWaitEvent(c.hs, c.evr, 0), "ordering the copy stream");
+    // the polls too: a poll that overtook the reset would read the PREVIOUS call's words ("every column final")
+    ck(cudaStreamWaitEvent(c.ps, c.evr, 0), "ordering the poll stream");
     for (int j0 = 0; j0 < q; j0 += ct) {
         const int nt = q - j0 < ct ? q - j0 : ct;
         ck(cudaMemcpy2DAsync(dA + (size_t)j0 * TB * m, sizeof(float) * m, mat + (size_t)j0 * TB * ldm, sizeof(float) * ldm,
