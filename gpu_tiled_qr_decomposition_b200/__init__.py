@@ -18,7 +18,7 @@ TASK_AVAIL, TASK_NONE, TASK_DONE = 0, 1, 2
 # every symbol include/qrb200.h and include/gpucalc_compat.h declare
 EXPORTS = (
     "b200qr_version", "b200qr_strerror", "b200qr_last_cuda_error", "b200qr_device_sm_count", "b200qr_copy",
-    "b200qr_measure_fp32_peak", "b200qr_probe_panel", "b200qr_probe_umma", "b200qr_probe_umma_rate", "b200qr_probe_umma_rate2",
+    "b200qr_measure_fp32_peak", "b200qr_probe_panel", "b200qr_probe_panel_chains", "b200qr_probe_umma", "b200qr_probe_umma_rate", "b200qr_probe_umma_rate2",
     "b200qr_plan_create", "b200qr_plan_destroy", "b200qr_plan_grid", "b200qr_plan_variant", "b200qr_plan_debug_counters", "b200qr_plan_tile_tasks",
     "b200qr_plan_macro_tasks", "b200qr_factor_device", "b200qr_plan_tau_device",
     "b200qr_tau_to_reference", "b200qr_factor_host", "b200qr_plan_read_trace", "b200qr_tile_task",

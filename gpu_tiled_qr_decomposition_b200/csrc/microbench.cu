@@ -132,3 +132,56 @@ extern "C" int b200qr_probe_panel(long long *cycles4, int reps)
     cudaFree(din); cudaFree(dout); cudaFree(dc); cudaFree(dstop);
     return B200QR_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// How many independent one-warp TSQRT chains does an SM run at full speed?  `nwarps` warps of one CTA (<= 16) each run
+// tsqrt_warp_v `reps` times on their own tile in shared memory; out[w] = SM cycles per tile seen by warp w.  (The
+// round-2 plan for tall-skinny QR -- one chain per warp and strip, DESIGN.md section 8 -- assumes eight chains per SM
+// run as fast as one: ~250 issued instructions per 470-cycle reflector step and two chains per scheduler.)
+namespace qrb200 {
+constexpr int CHAIN_FLOATS = TB * 33 + 2 * TB + 2 * TB * TB + 24;       // Rs, xs, tile, V2 out (+ pad to 16 bytes)
+__global__ void __launch_bounds__(512) panel_chains_kernel(const float *tile_in, float *sink, long long *cycles, int reps)
+{
+    extern __shared__ __align__(16) float csm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *Rs = csm + (size_t)warp * CHAIN_FLOATS;
+    float *xs = Rs + TB * 33 + 8;                                        // 16-byte aligned: (33 * 32 + 8) * 4 = 4256
+    float *ts = xs + 2 * TB;
+    float *ts2 = ts + TB * TB;
+    float a[TB], b[TB];
+    load_col_gmem(a, tile_in + lane * TB);
+    store_col_smem(ts + lane * TB, a);
+#pragma unroll
+    for (int r = 0; r < TB; ++r) Rs[r * 33 + lane] = (r <= lane) ? a[r] + (r == lane ? 8.0f : 0.f) : 0.f;   // a triangle with a healthy diagonal
+    __syncthreads();
+    const long long t0 = clock64();
+    float acc = 0.f;
+    for (int r = 0; r < reps; ++r) {
+        load_col_smem(b, ts + lane * TB);
+        acc += tsqrt_warp_v<false>(b, Rs, xs, ts2, lane);
+    }
+    const long long t1 = clock64();
+    if (lane == 0) { cycles[warp] = (t1 - t0) / reps; sink[warp] = acc; }
+}
+}  // namespace qrb200
+
+extern "C" int b200qr_probe_panel_chains(long long *cycles, int reps, int nwarps)
+{
+    if (!cycles || reps <= 0 || nwarps < 1 || nwarps > 16) return B200QR_EINVAL;
+    float h[32 * 32];
+    for (int i = 0; i < 1024; ++i) h[i] = (float)((i * 37 % 201) - 100) / 100.0f;
+    float *din = nullptr, *dsink = nullptr;
+    long long *dc = nullptr;
+    if (cudaMalloc(&din, 4096) || cudaMalloc(&dsink, 64 * 4) || cudaMalloc(&dc, 16 * 8)) return B200QR_ECUDA;
+    cudaMemcpy(din, h, 4096, cudaMemcpyHostToDevice);
+    const int smem = nwarps * qrb200::CHAIN_FLOATS * (int)sizeof(float);
+    int rc = B200QR_OK;
+    if (cudaFuncSetAttribute(qrb200::panel_chains_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) rc = B200QR_ECUDA;
+    if (rc == B200QR_OK) {
+        qrb200::panel_chains_kernel<<<1, nwarps * 32, smem>>>(din, dsink, dc, reps);
+        if (cudaDeviceSynchronize() != cudaSuccess) rc = B200QR_ECUDA;
+        else cudaMemcpy(cycles, dc, sizeof(long long) * nwarps, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(din); cudaFree(dsink); cudaFree(dc);
+    return rc;
+}

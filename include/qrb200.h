@@ -76,6 +76,9 @@ int         b200qr_measure_fp32_peak(double *gflops, int iters);
 /* SM cycles per tile of the panel kernels run by one warp: cycles4 = {GEQRT alone, TSQRT alone,
  * GEQRT / TSQRT with eight FFMA-bound warps on the same SM}.  Diagnostic for the scheduler design. */
 int         b200qr_probe_panel(long long *cycles4, int reps);
+/* SM cycles per tile of `nwarps` (<= 16) independent one-warp TSQRT chains sharing one SM: cycles[w] for warp w.  Diagnostic
+ * for the tall-skinny plan of DESIGN.md section 8 (how many chains an SM runs at the speed of one). */
+int b200qr_probe_panel_chains(long long *cycles, int reps, int nwarps);
 /* tcgen05 building-block check (see csrc/umma_probe.cu): hA 32 x 128 column-major, hV 32 x 32 column-major,
  * hW 128 x 32 row-major or NULL; hZ <- A^T V (128 x 32 row-major, 3xTF32 on the tensor cores);
  * hD2 <- A^T - W V^T when hW is given. */
