@@ -18,7 +18,7 @@ TASK_AVAIL, TASK_NONE, TASK_DONE = 0, 1, 2
 # every symbol include/qrb200.h and include/gpucalc_compat.h declare
 EXPORTS = (
     "b200qr_version", "b200qr_strerror", "b200qr_last_cuda_error", "b200qr_device_sm_count", "b200qr_copy",
-    "b200qr_measure_fp32_peak", "b200qr_probe_panel", "b200qr_probe_panel_chains", "b200qr_probe_umma", "b200qr_probe_umma_rate", "b200qr_probe_umma_rate2",
+    "b200qr_measure_fp32_peak",
     "b200qr_plan_create", "b200qr_plan_destroy", "b200qr_plan_grid", "b200qr_plan_variant", "b200qr_plan_debug_counters", "b200qr_plan_tile_tasks",
     "b200qr_plan_macro_tasks", "b200qr_factor_device", "b200qr_plan_tau_device",
     "b200qr_tau_to_reference", "b200qr_factor_host", "b200qr_plan_read_trace", "b200qr_tile_task",
@@ -45,20 +45,49 @@ class Task(C.Structure):
 
 
 class Opts(C.Structure):
-    _fields_ = [("grid_ctas", C.c_int), ("trace", C.c_int), ("share_device", C.c_int), ("reserved", C.c_int * 5)]
+    _fields_ = [("grid_ctas", C.c_int), ("trace", C.c_int), ("share_device", C.c_int), ("engine", C.c_int),
+                ("reserved", C.c_int * 4)]
+
+
+PROBE_LIB_PATH = os.path.join(HERE, "libqrb200_probe.so")     # diagnostics (tools/qrb200_probe.h), not the product ABI
 
 
 def build(force=False):
-    """Compile libqrb200.so in-tree with nvcc for sm_100a (no GPU needed)."""
-    srcs = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))]
+    """Compile libqrb200.so (and the diagnostics library) in-tree with nvcc for sm_100a (no GPU needed)."""
+    srcs = []
+    for d, _, fs in os.walk(os.path.join(HERE, "csrc")):
+        srcs += [os.path.join(d, f) for f in fs]
     srcs.append(os.path.join(os.path.dirname(HERE), "include", "qrb200.h"))
-    stale = force or not os.path.exists(LIB_PATH) or any(
-        os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    srcs.append(os.path.join(os.path.dirname(HERE), "tools", "qrb200_probe.h"))
+    srcs.append(os.path.join(HERE, "Makefile"))
+    here_lib = os.path.join(HERE, "libqrb200.so")
+    stale = force or any(not os.path.exists(l) or any(os.path.getmtime(s) > os.path.getmtime(l) for s in srcs)
+                         for l in (here_lib, PROBE_LIB_PATH))
     if stale:
-        r = subprocess.run(["make", "-C", HERE, "libqrb200.so"], capture_output=True, text=True)
+        r = subprocess.run(["make", "-C", HERE, "all"], capture_output=True, text=True)
         if r.returncode != 0:
             raise QRError("building libqrb200.so failed:\n" + r.stdout + r.stderr)
     return LIB_PATH
+
+
+_probe = None
+
+
+def probe_lib():
+    """The diagnostics library (panel-latency and tcgen05 probes)."""
+    global _probe
+    if _probe is None:
+        if not os.path.exists(PROBE_LIB_PATH):
+            raise QRError("libqrb200_probe.so is not built")
+        P = C.CDLL(PROBE_LIB_PATH)
+        vp = C.c_void_p
+        P.b200qr_probe_panel.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), vp]
+        P.b200qr_probe_umma.argtypes = [vp, vp, vp, vp, vp]
+        P.b200qr_probe_umma_mode.argtypes = [vp, vp, vp, vp, vp, C.c_int]
+        P.b200qr_probe_umma_rate.argtypes = [C.POINTER(C.c_longlong), C.c_int]
+        P.b200qr_probe_umma_rate2.argtypes = [C.POINTER(C.c_longlong), C.c_int]
+        _probe = P
+    return _probe
 
 
 _lib = None
@@ -77,8 +106,6 @@ def lib():
         L.b200qr_strerror.argtypes = [C.c_int]
         L.b200qr_copy.argtypes = [vp, vp, C.c_size_t]
         L.b200qr_measure_fp32_peak.argtypes = [C.POINTER(C.c_double), C.c_int]
-        L.b200qr_probe_panel.argtypes = [C.POINTER(C.c_longlong), C.c_int]
-        L.b200qr_probe_umma.argtypes = [vp, vp, vp, vp, vp]
         L.b200qr_plan_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(Opts)]
         L.b200qr_plan_destroy.argtypes = [vp]
         L.b200qr_plan_grid.argtypes = [vp]
@@ -164,11 +191,12 @@ def check(rc, what="libqrb200"):
 class Plan:
     """Workspace + schedule for one (m, n) shape (b200qr_plan_*)."""
 
-    def __init__(self, m, n, grid_ctas=0, trace=False):
+    def __init__(self, m, n, grid_ctas=0, trace=False, engine=0):
+        """engine: 0 = automatic, 1 = FP32 SIMT sweeps, 2 = tensor-core sweeps (b200qr_opts.engine)."""
         self.m, self.n = m, n
         self._h = C.c_void_p()
         o = Opts()
-        o.grid_ctas, o.trace = int(grid_ctas), int(trace)
+        o.grid_ctas, o.trace, o.engine = int(grid_ctas), int(trace), int(engine)
         check(lib().b200qr_plan_create(C.byref(self._h), m, n, C.byref(o)), "b200qr_plan_create")
 
     @property
@@ -264,11 +292,11 @@ def device_order(M, N):
 class DistRank:
     """One rank of the 1-D block-cyclic multi-GPU factorisation (b200qr_dist_*)."""
 
-    def __init__(self, m, n, rank, world, share_device=0, grid_ctas=0, trace=0):
+    def __init__(self, m, n, rank, world, share_device=0, grid_ctas=0, trace=0, engine=0):
         self.m, self.n, self.rank, self.world = m, n, rank, world
         self._h = C.c_void_p()
         o = Opts()
-        o.grid_ctas, o.share_device, o.trace = int(grid_ctas), int(share_device), int(trace)
+        o.grid_ctas, o.share_device, o.trace, o.engine = int(grid_ctas), int(share_device), int(trace), int(engine)
         check(lib().b200qr_dist_create(C.byref(self._h), m, n, rank, world, C.byref(o)), "b200qr_dist_create")
         self.block = lib().b200qr_dist_block(self._h)
 

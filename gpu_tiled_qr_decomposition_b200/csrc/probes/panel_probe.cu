@@ -1,0 +1,105 @@
+// panel_probe.cu -- latency / throughput probes of the one-warp panel kernels (diagnostics library
+// libqrb200_probe.so, tools/qrb200_probe.h; not part of the product ABI).
+#include "../qr_device.cuh"
+#include "../../../tools/qrb200_probe.h"
+#include <cuda_runtime.h>
+
+namespace qrb200 {
+
+constexpr int CHAIN_FLOATS = TB * 33 + 2 * TB + 2 * TB * TB + 24;       // Rs, xs, tile, V2 out (+ pad to 16 bytes)
+
+// `nwarps` warps of one CTA each run GEQRT `reps` times, then TSQRT `reps` times, on their own tile in shared memory;
+// cycles[2w] / cycles[2w + 1] = SM cycles per GEQRT / TSQRT tile seen by warp w.  out: warp 0's last GEQRT tile, R and V2
+// (3 x 1024 floats) so the variants can be compared on the host.  busy != 0: eight more warps run an FFMA loop.
+__global__ void __launch_bounds__(512) panel_probe_kernel(const float *tile_in, float *out, long long *cycles, int reps, int nwarps,
+                                                          int busy, volatile int *stop)
+{
+    extern __shared__ __align__(16) float csm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < nwarps) {
+        float *Rs = csm + (size_t)warp * CHAIN_FLOATS;
+        float *xs = Rs + TB * 33 + 8;
+        float *ts = xs + 2 * TB;
+        float *ts2 = ts + TB * TB;
+        float a[TB], b[TB];
+        load_col_gmem(a, tile_in + lane * TB);
+        store_col_smem(ts + lane * TB, a);
+        __syncwarp();
+        float acc = 0.f;
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+            load_col_smem(a, ts + lane * TB);
+            acc += geqrt_warp(a, xs, lane);
+        }
+        const long long t1 = clock64();
+        if (warp == 0) store_col_gmem(out + lane * TB, a);
+#pragma unroll
+        for (int r = 0; r < TB; ++r) Rs[r * 33 + lane] = a[r];
+        __syncwarp();
+        for (int r = 0; r < reps; ++r) {
+            if (r > 0) {                                     // keep the triangle bounded over many repetitions
+#pragma unroll
+                for (int q = 0; q < TB; ++q) Rs[q * 33 + lane] = a[q];
+                __syncwarp();
+            }
+            load_col_smem(b, ts + lane * TB);
+            acc += tsqrt_warp_v<false>(b, Rs, xs, ts2, lane);
+        }
+        const long long t2 = clock64();
+        if (warp == 0) {
+#pragma unroll
+            for (int r = 0; r < TB; ++r) out[TB * TB + lane * TB + r] = Rs[r * 33 + lane];
+            load_col_smem(b, ts2 + lane * TB);
+            store_col_gmem(out + 2 * TB * TB + lane * TB, b);
+        }
+        if (lane == 0) { cycles[2 * warp] = (t1 - t0) / reps; cycles[2 * warp + 1] = (t2 - t1) / reps; out[3 * TB * TB + warp] = acc; }
+        __syncwarp();
+        if (warp == 0 && lane == 0) *stop = 1;
+    } else if (busy) {
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = (float)(threadIdx.x + i);
+        while (*stop == 0) {
+#pragma unroll
+            for (int u = 0; u < 64; ++u)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = fmaf(acc[i], 1.0000001f, 1e-7f);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += acc[i];
+        if (s == 12345.678f) out[3 * TB * TB + 63] = s;
+    }
+}
+
+}  // namespace qrb200
+
+extern "C" int b200qr_probe_panel(int nwarps, int busy, int reps, long long *cycles, float *out3)
+{
+    using namespace qrb200;
+    if (!cycles || reps <= 0 || nwarps < 1 || nwarps > 16 || (busy && nwarps > 8)) return -1;
+    float h[32 * 32];
+    unsigned lcg = 12345u;                                   // a full-rank pseudo-random tile on the reference's 201-point grid
+    for (int i = 0; i < 1024; ++i) { lcg = lcg * 1664525u + 1013904223u; h[i] = (float)((int)((lcg >> 8) % 201u) - 100) / 100.0f; }
+    float *din = nullptr, *dout = nullptr;
+    long long *dc = nullptr;
+    int *dstop = nullptr;
+    if (cudaMalloc(&din, 4096) || cudaMalloc(&dout, (3 * 1024 + 64) * 4) || cudaMalloc(&dc, 32 * 8) || cudaMalloc(&dstop, 4)) return -2;
+    cudaMemcpy(din, h, 4096, cudaMemcpyHostToDevice);
+    cudaMemset(dstop, 0, 4);
+    cudaMemset(dout, 0, (3 * 1024 + 64) * 4);
+    const int smem = nwarps * CHAIN_FLOATS * (int)sizeof(float);
+    const int threads = (nwarps + (busy ? 8 : 0)) * 32;
+    int rc = 0;
+    if (cudaFuncSetAttribute(panel_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) rc = -2;
+    if (rc == 0) {
+        panel_probe_kernel<<<1, threads, smem>>>(din, dout, dc, reps, nwarps, busy, dstop);
+        if (cudaDeviceSynchronize() != cudaSuccess) rc = -2;
+    }
+    if (rc == 0) {
+        cudaMemcpy(cycles, dc, sizeof(long long) * 2 * nwarps, cudaMemcpyDeviceToHost);
+        if (out3) cudaMemcpy(out3, dout, 3 * 1024 * 4, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(din); cudaFree(dout); cudaFree(dc); cudaFree(dstop);
+    return rc;
+}

@@ -7,8 +7,9 @@
 //   product of the compact-WY update) from a 128 x 32 W.  Both B operands are K-major: V for the first
 //   product, a transposed copy V^T (made during the hi/lo split) for the second -- tcgen05.mma returned
 //   zeros on B200 when the same tile was described as an MN-major tf32 operand.
-#include "qr_umma.cuh"
-#include "../../include/qrb200.h"
+#include "../qr_umma.cuh"
+#include "../../../include/qrb200.h"
+#include "../../../tools/qrb200_probe.h"
 
 namespace qrb200 {
 

@@ -350,314 +350,9 @@ __global__ void __launch_bounds__(256, MINB) tsqr_strip_kernel(const StripArgs a
 }
 
 
-// Same kernel with a shorter per-reflector chain: the next owner broadcasts its column the moment it is updated
-// (before its sum of squares, rsqrt and reciprocal), and the step has two barriers -- (A) column visible, (B) Householder
-// scalars visible -- so every other warp's dot product with the new column overlaps the owner's scalar work.
-// MEASURED (B200, 4 194 304 x 256): 56.9 ms (48-row blocks) / 51.7 ms (32-row blocks, 3 CTAs per SM) against 48.0 ms for
-// the one-barrier kernel -- same numbers bit for bit, but the second barrier costs more than the overlap returns: with
-// two or three CTAs per SM the other CTAs already fill the owner's scalar work.  Kept behind QRB200_TSQR_EARLY=1.
-template <int SRB, int MINB, bool TRI>
-__global__ void __launch_bounds__(256, MINB) tsqr_strip_early_kernel(const StripArgs a)
-{
-    __shared__ __align__(16) float xs[2 * SRB];             // two broadcast slots
-    __shared__ float hs[4];                                 // two slots of {1/piv, tau}
-    const int n = a.n, j = threadIdx.x;
-    float *Rg = a.Rws + (size_t)blockIdx.x * (n * (n + 1) / 2);    // (c, col) at c*n - c*(c-1)/2 + (col - c)
-    const long long row0 = (long long)blockIdx.x * a.rows_per_strip;
-    long long row1 = row0 + a.rows_per_strip;
-    if (row1 > a.rows) row1 = a.rows;
-    float *col = a.A + (size_t)j * a.ldm;
-    float *tau_out = a.tau + (size_t)blockIdx.x * a.blocks_per_strip * n;
-    if (TRI) {                                              // thread j: column j of the first factor -> its triangle
-        for (int c = 0; c <= j; ++c) __stcg(Rg + c * n - (c * (c - 1)) / 2 + (j - c), col[row0 + c]);
-    }
-
-    for (long long r0 = row0 + (TRI ? n : 0); r0 < row1; r0 += SRB, tau_out += n) {
-        const int nr = (int)(row1 - r0 < SRB ? row1 - r0 : SRB);     // a multiple of 4
-        const int c0 = TRI ? (int)((r0 - row0) % n) : 0;    // first column of this block that is not all zeros
-        float rc_next = 0.f;                                // R(c0, j): this thread's own store of an earlier block
-        if (j >= c0) rc_next = __ldcg(Rg + c0 * n - (c0 * (c0 - 1)) / 2 + (j - c0));
-        float b[SRB];
-#pragma unroll
-        for (int r = 0; r < SRB; r += 4) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < nr) v = __ldcs(reinterpret_cast<const float4 *>(col + r0 + r));
-            b[r] = v.x; b[r + 1] = v.y; b[r + 2] = v.z; b[r + 3] = v.w;
-        }
-        auto sumsq = [&]() {
-            float s[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) s[i] = b[i] * b[i];
-#pragma unroll
-            for (int r = 8; r < SRB; r += 8)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) s[i] = fmaf(b[r + i], b[r + i], s[i]);
-            return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
-        };
-        if (j == c0) {                                      // the block's first owner broadcasts its column right away
-            float *x0 = xs + (c0 & 1) * SRB;
-#pragma unroll
-            for (int r = 0; r < SRB; r += 4) *reinterpret_cast<float4 *>(x0 + r) = make_float4(b[r], b[r + 1], b[r + 2], b[r + 3]);
-        }
-#pragma unroll 1
-        for (int c = c0; c < n; ++c) {
-            float *x = xs + (c & 1) * SRB;
-            float *h2 = hs + (c & 1) * 2;
-            const int off = c * n - (c * (c - 1)) / 2;
-            const float rc = rc_next;                       // R(c, j), valid for j >= c
-            if (j > c) rc_next = __ldcg(Rg + off + (n - c) + (j - c - 1));     // R(c + 1, j): in flight during this step
-            __syncthreads();                                // (A) x_c is visible
-            if (j == c) {                                   // owner: Householder scalars, while the others do their dot products
-                const HouseScalars h = house_scalars(rc, sumsq());
-                h2[0] = h.inv; h2[1] = h.tau;
-                tau_out[c] = h.tau;
-            }
-            float d = 0.f;
-            if (j >= c) {
-                float s[8];
-#pragma unroll
-                for (int i = 0; i < 8; i += 4) {
-                    const float4 xv = *reinterpret_cast<const float4 *>(x + i);
-                    s[i] = b[i] * xv.x; s[i + 1] = b[i + 1] * xv.y; s[i + 2] = b[i + 2] * xv.z; s[i + 3] = b[i + 3] * xv.w;
-                }
-#pragma unroll
-                for (int r = 8; r < SRB; r += 8)
-#pragma unroll
-                    for (int i = 0; i < 8; i += 4) {
-                        const float4 xv = *reinterpret_cast<const float4 *>(x + r + i);
-                        s[i] = fmaf(b[r + i], xv.x, s[i]); s[i + 1] = fmaf(b[r + i + 1], xv.y, s[i + 1]);
-                        s[i + 2] = fmaf(b[r + i + 2], xv.z, s[i + 2]); s[i + 3] = fmaf(b[r + i + 3], xv.w, s[i + 3]);
-                    }
-                d = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
-            }
-            __syncthreads();                                // (B) (1/piv, tau) of reflector c are visible
-            const float inv = h2[0], tau = h2[1];
-            // the reflector replaces column c of the block
-            {
-                float *vcol = a.A + (size_t)c * a.ldm + r0;
-                for (int t = j; t < nr; t += n) vcol[t] = x[t] * inv;
-            }
-            if (j >= c) {
-                // beta = tau (R(c,j) + v' B(:,j)),  v = x / piv
-                const float beta = tau * fmaf(inv, d, rc);
-                __stcg(Rg + off + j - c, rc - beta);
-                if (j > c) {
-                    const float g = -beta * inv;
-#pragma unroll
-                    for (int r = 0; r < SRB; r += 4) {
-                        const float4 xv = *reinterpret_cast<const float4 *>(x + r);
-                        b[r] = fmaf(g, xv.x, b[r]); b[r + 1] = fmaf(g, xv.y, b[r + 1]);
-                        b[r + 2] = fmaf(g, xv.z, b[r + 2]); b[r + 3] = fmaf(g, xv.w, b[r + 3]);
-                    }
-                    if (j == c + 1) {                       // the next owner broadcasts its column at once: the other warps'
-                        float *xn = xs + ((c + 1) & 1) * SRB;       // dot products then overlap its sum of squares / rsqrt / rcp
-#pragma unroll
-                        for (int r = 0; r < SRB; r += 4) *reinterpret_cast<float4 *>(xn + r) = make_float4(b[r], b[r + 1], b[r + 2], b[r + 3]);
-                    }
-                }
-            }
-        }
-    }
-    float *rcol = a.Rout + (size_t)j * a.ldr + (size_t)blockIdx.x * n;
-    for (int c = 0; c < n; ++c) rcol[c] = (c <= j) ? __ldcg(Rg + c * n - (c * (c - 1)) / 2 + (j - c)) : 0.f;
-}
-
-
-// ---- the same recurrence, WNB reflectors per barrier (compact-WY inside the block) -----------------------------------
-// The one-reflector-per-barrier kernel above keeps all eight warps on the per-reflector chain.  Here the warp that owns
-// the next WNB columns factors them by itself (phase A: the same steps, but __syncwarp instead of a CTA barrier, and
-// only its own 32 columns are updated), leaving in shared memory the WNB broadcast columns x_k, their (1/piv, tau) and
-// the Gram entries G(k,l) = x_k . x_l (l < k).  After ONE barrier the warps to its right apply the WNB reflectors in a
-// single sweep over their block columns (phase B):
-//     d_k = x_k . b                                   (one pass, WNB independent accumulators)
-//     beta_k = tau_k (R(c+k, j) + inv_k (d_k + sum_{l<k} g_l G(k,l))),   g_k = -beta_k inv_k     (scalar recurrence)
-//     b += sum_k g_k x_k                               (one pass)
-// which is the sequential application H_{k} ... H_0 written out (x_k . b^(k) = d_k + sum_{l<k} g_l G(k,l)).  The owner
-// warp does not wait for them: it goes straight on to the next WNB columns (double-buffered panel slots), so phase B
-// of panel P overlaps phase A of panel P + 1 and only one warp at a time sits on the serial chain.
-// MEASURED (B200, 4 194 304 x 256): 58.9 ms against 48.0 ms for the kernel above -- correct (same tests), but slower:
-// the in-warp step costs as much as the CTA-wide one (~900 cycles: dot, update and sum-of-squares passes of the owner
-// warp plus rsqrt / rcp, not the barrier, make the chain), and phase B adds the Gram dots and the warp hand-overs.  Kept
-// behind QRB200_TSQR_NB=8 as the starting point for a shorter chain; the default is one reflector per barrier.
-constexpr int WNB = 8;
-
-template <int SRB, int MINB, bool TRI>
-__global__ void __launch_bounds__(256, MINB) tsqr_strip_wy_kernel(const StripArgs a)
-{
-    constexpr int XS = SRB + 4;                             // slot stride: 16-byte aligned, conflict-free for the Gram dots
-    __shared__ __align__(16) float xs[2][WNB][XS];          // [panel parity][k][row]
-    __shared__ float hsv[2][WNB][2];                        // {1/piv, tau}
-    __shared__ float gs[2][WNB][WNB];                       // gs[.][k][l] = x_k . x_l, l < k
-    const int n = a.n, j = threadIdx.x, warp = j >> 5, lane = j & 31;
-    float *Rg = a.Rws + (size_t)blockIdx.x * (n * (n + 1) / 2);    // (c, col) at c*n - c*(c-1)/2 + (col - c)
-    const long long row0 = (long long)blockIdx.x * a.rows_per_strip;
-    long long row1 = row0 + a.rows_per_strip;
-    if (row1 > a.rows) row1 = a.rows;
-    float *col = a.A + (size_t)j * a.ldm;
-    float *tau_out = a.tau + (size_t)blockIdx.x * a.blocks_per_strip * n;
-    if (TRI) {                                              // thread j: column j of the first factor -> its triangle
-        for (int c = 0; c <= j; ++c) __stcg(Rg + c * n - (c * (c - 1)) / 2 + (j - c), col[row0 + c]);
-    }
-    unsigned pi = 0;                                        // running panel count: its parity picks the slot set
-
-    for (long long r0 = row0 + (TRI ? n : 0); r0 < row1; r0 += SRB, tau_out += n) {
-        const int nr = (int)(row1 - r0 < SRB ? row1 - r0 : SRB);     // a multiple of 4
-        const int c0 = TRI ? (int)((r0 - row0) % n) : 0;    // first column of this block that is not all zeros (multiple of 32)
-        float rc_next = 0.f;
-        if (j >= c0) rc_next = __ldcg(Rg + c0 * n - (c0 * (c0 - 1)) / 2 + (j - c0));
-        float b[SRB];
-#pragma unroll
-        for (int r = 0; r < SRB; r += 4) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < nr) v = __ldcs(reinterpret_cast<const float4 *>(col + r0 + r));
-            b[r] = v.x; b[r + 1] = v.y; b[r + 2] = v.z; b[r + 3] = v.w;
-        }
-        auto sumsq = [&]() {
-            float s[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) s[i] = b[i] * b[i];
-#pragma unroll
-            for (int r = 8; r < SRB; r += 8)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) s[i] = fmaf(b[r + i], b[r + i], s[i]);
-            return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
-        };
-        float ssq = sumsq();
-
-#pragma unroll 1
-        for (int c = c0; c < n; c += WNB, ++pi) {
-            const int par = pi & 1;
-            const int W = c >> 5;
-            if (warp == W) {
-                // ---- phase A: this warp factors columns c .. c + WNB - 1 and keeps its own 32 columns up to date
-#pragma unroll 1
-                for (int k = 0; k < WNB; ++k) {
-                    const int cc = c + k;
-                    float *x = &xs[par][k][0];
-                    const int off = cc * n - (cc * (cc - 1)) / 2;
-                    const float rc = rc_next;               // R(cc, j), valid for j >= cc
-                    if (j == cc) {
-#pragma unroll
-                        for (int r = 0; r < SRB; r += 4) *reinterpret_cast<float4 *>(x + r) = make_float4(b[r], b[r + 1], b[r + 2], b[r + 3]);
-                        const HouseScalars h = house_scalars(rc, ssq);
-                        hsv[par][k][0] = h.inv; hsv[par][k][1] = h.tau;
-                        tau_out[cc] = h.tau;
-                    }
-                    if (j > cc && cc + 1 < n) rc_next = __ldcg(Rg + off + (n - cc) + (j - cc - 1));   // R(cc + 1, j)
-                    __syncwarp();
-                    const float inv = hsv[par][k][0], tau = hsv[par][k][1];
-                    if (j >= cc) {
-                        float s[8];
-#pragma unroll
-                        for (int i = 0; i < 8; i += 4) {
-                            const float4 xv = *reinterpret_cast<const float4 *>(x + i);
-                            s[i] = b[i] * xv.x; s[i + 1] = b[i + 1] * xv.y; s[i + 2] = b[i + 2] * xv.z; s[i + 3] = b[i + 3] * xv.w;
-                        }
-#pragma unroll
-                        for (int r = 8; r < SRB; r += 8)
-#pragma unroll
-                            for (int i = 0; i < 8; i += 4) {
-                                const float4 xv = *reinterpret_cast<const float4 *>(x + r + i);
-                                s[i] = fmaf(b[r + i], xv.x, s[i]); s[i + 1] = fmaf(b[r + i + 1], xv.y, s[i + 1]);
-                                s[i + 2] = fmaf(b[r + i + 2], xv.z, s[i + 2]); s[i + 3] = fmaf(b[r + i + 3], xv.w, s[i + 3]);
-                            }
-                        const float d = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
-                        const float beta = tau * fmaf(inv, d, rc);
-                        __stcg(Rg + off + j - cc, rc - beta);
-                        if (j > cc) {
-                            const float g = -beta * inv;
-#pragma unroll
-                            for (int r = 0; r < SRB; r += 4) {
-                                const float4 xv = *reinterpret_cast<const float4 *>(x + r);
-                                b[r] = fmaf(g, xv.x, b[r]); b[r + 1] = fmaf(g, xv.y, b[r + 1]);
-                                b[r + 2] = fmaf(g, xv.z, b[r + 2]); b[r + 3] = fmaf(g, xv.w, b[r + 3]);
-                            }
-                            ssq = sumsq();                  // lane cc + 1 needs it next
-                        }
-                    }
-                }
-                // Gram entries G(k, l) = x_k . x_l of the panel, one pair per lane (28 pairs), straight from shared memory
-                __syncwarp();
-                if (lane < WNB * (WNB - 1) / 2) {
-                    int k = 1, l = lane;
-                    while (l >= k) { l -= k; ++k; }          // lane -> (k, l), l < k
-                    const float *xk = &xs[par][k][0], *xl = &xs[par][l][0];
-                    float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
-#pragma unroll 4
-                    for (int r = 0; r < SRB; r += 4) {
-                        const float4 u = *reinterpret_cast<const float4 *>(xk + r);
-                        const float4 v = *reinterpret_cast<const float4 *>(xl + r);
-                        g0 = fmaf(u.x, v.x, g0); g1 = fmaf(u.y, v.y, g1); g2 = fmaf(u.z, v.z, g2); g3 = fmaf(u.w, v.w, g3);
-                    }
-                    gs[par][k][l] = (g0 + g1) + (g2 + g3);
-                }
-            }
-            __syncthreads();                                // panel c is complete in xs / hsv / gs [par]
-            // the reflectors replace columns c .. c + WNB - 1 of the block (everyone helps, idle warps included)
-            for (int idx = j; idx < WNB * nr; idx += n) {
-                const int k = idx / nr, t = idx - k * nr;
-                a.A[(size_t)(c + k) * a.ldm + r0 + t] = xs[par][k][t] * hsv[par][k][0];
-            }
-            if (warp > W) {
-                // ---- phase B: the WNB reflectors applied to this thread's block column in one sweep
-                float rr[WNB];
-                {
-                    int off = c * n - (c * (c - 1)) / 2 + (j - c);
-#pragma unroll
-                    for (int k = 0; k < WNB; ++k) { rr[k] = __ldcg(Rg + off); off += n - (c + k) - 1; }
-                }
-                const bool next_owner = c + WNB < n && warp == ((c + WNB) >> 5);
-                if (next_owner) {
-                    const int cn = c + WNB;
-                    rc_next = __ldcg(Rg + cn * n - (cn * (cn - 1)) / 2 + (j - cn));
-                }
-                float d[WNB];
-#pragma unroll
-                for (int k = 0; k < WNB; ++k) d[k] = 0.f;
-                // (the __syncwarp() per chunk of four rows is a scheduling fence: without it ptxas hoists all 8 x SRB/4
-                //  shared-memory loads of a pass to its top and spills ~1.4 KB per thread under the 128-register cap)
-#pragma unroll
-                for (int r = 0; r < SRB; r += 4) {
-#pragma unroll
-                    for (int k = 0; k < WNB; ++k) {
-                        const float4 xv = *reinterpret_cast<const float4 *>(&xs[par][k][r]);
-                        d[k] = fmaf(b[r], xv.x, d[k]); d[k] = fmaf(b[r + 1], xv.y, d[k]);
-                        d[k] = fmaf(b[r + 2], xv.z, d[k]); d[k] = fmaf(b[r + 3], xv.w, d[k]);
-                    }
-                    __syncwarp();
-                }
-                float g[WNB];
-                {
-                    int off = c * n - (c * (c - 1)) / 2 + (j - c);
-#pragma unroll
-                    for (int k = 0; k < WNB; ++k) {
-                        float acc = d[k];
-#pragma unroll
-                        for (int l = 0; l < k; ++l) acc = fmaf(g[l], gs[par][k][l], acc);
-                        const float inv = hsv[par][k][0], tau = hsv[par][k][1];
-                        const float beta = tau * fmaf(inv, acc, rr[k]);
-                        __stcg(Rg + off, rr[k] - beta);
-                        off += n - (c + k) - 1;
-                        g[k] = -beta * inv;
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < SRB; r += 4) {
-#pragma unroll
-                    for (int k = 0; k < WNB; ++k) {
-                        const float4 xv = *reinterpret_cast<const float4 *>(&xs[par][k][r]);
-                        b[r] = fmaf(g[k], xv.x, b[r]); b[r + 1] = fmaf(g[k], xv.y, b[r + 1]);
-                        b[r + 2] = fmaf(g[k], xv.z, b[r + 2]); b[r + 3] = fmaf(g[k], xv.w, b[r + 3]);
-                    }
-                    __syncwarp();
-                }
-                if (next_owner) ssq = sumsq();
-            }
-        }
-    }
-    float *rcol = a.Rout + (size_t)j * a.ldr + (size_t)blockIdx.x * n;
-    for (int c = 0; c < n; ++c) rcol[c] = (c <= j) ? __ldcg(Rg + c * n - (c * (c - 1)) / 2 + (j - c)) : 0.f;
-}
+// Two variants of this kernel were measured in round 1 and removed in round 2 (profiles/r1_measurements.md): a
+// two-barrier form in which the next owner broadcasts its column before its scalar work (56.9 ms against 48.0 ms at
+// 4 194 304 x 256) and a form with eight reflectors per barrier and a compact-WY sweep by the other warps (58.9 ms).
 
 }  // namespace qrb200
 
@@ -673,9 +368,11 @@ static thread_local int g_batched_cuda = 0;
 static int batched_launch(float *dA, int m, int n, int ldm, long long strideA, int nprob, float *dTau, int *dCounter,
                           cudaStream_t stream)
 {
-    static int grid_cap = 0;
+    // the shared-memory opt-in is a per-device attribute and the grid cap a per-device number: both are taken for the
+    // CURRENT device on every call (two cheap runtime calls), so a process may use several GPUs and threads
     const int smem = BQ * WARP_FLOATS * (int)sizeof(float);
-    if (!grid_cap) {
+    int grid_cap = 0;
+    {
         int dev = 0, sms = 0, occ = 0;
         CKB(cudaGetDevice(&dev));
         CKB(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -709,8 +406,6 @@ struct b200qr_tsqr_s {
     struct SLevel { int count; float *stack = nullptr, *tau = nullptr; };
     std::vector<SLevel> slevels;
     bool rstack = false;                // b200qr_tsqr_create_rstack: the input IS level 0's stack of factors
-    bool early = false;                 // QRB200_TSQR_EARLY=1: two-barrier variant (measured slower, see tsqr_strip_early_kernel)
-    bool wy = false;                    // QRB200_TSQR_NB=8: WNB reflectors per barrier (measured slower, see tsqr_strip_wy_kernel)
     bool streaming = false;
 };
 
@@ -824,8 +519,6 @@ int b200qr_tsqr_create_rstack(b200qr_tsqr_t *out, int count, int n)
     b200qr_tsqr_s *t = new b200qr_tsqr_s;
     t->m = (long long)count * n; t->n = n; t->leaf_rows = 0; t->fanin = 2; t->streaming = true; t->rstack = true;
     t->strips = count;
-    if (const char *e = getenv("QRB200_TSQR_NB")) t->wy = atoi(e) == WNB;
-    if (const char *e = getenv("QRB200_TSQR_EARLY")) t->early = atoi(e) != 0;
     auto fail = [&]() { b200qr_tsqr_destroy(t); return B200QR_ENOMEM; };
     if (cudaMalloc(&t->d_rws, sizeof(float) * (size_t)((count + 1) / 2) * (n * (n + 1) / 2)) != cudaSuccess) return fail();
     if (build_slevels(t, count, true) != B200QR_OK) return fail();
@@ -849,11 +542,8 @@ int b200qr_tsqr_create_streaming(b200qr_tsqr_t *out, long long m, int n, int str
     t->m = m; t->n = n; t->leaf_rows = 0; t->fanin = 4; t->streaming = true;
     auto fail = [&]() { b200qr_tsqr_destroy(t); return B200QR_ENOMEM; };
     if (const char *e = getenv("QRB200_TSQR_RB")) { const int v = atoi(e); if (v == 32 || v == 48 || v == 64) t->srb = v; }
-    if (const char *e = getenv("QRB200_TSQR_NB")) t->wy = atoi(e) == WNB;
-    if (const char *e = getenv("QRB200_TSQR_EARLY")) t->early = atoi(e) != 0;
-    if ((t->wy || t->early) && t->srb == 64) t->srb = 48;
     const int SRB = t->srb;
-    if (strips_auto) strips = sms * (SRB == 32 && !t->wy ? 3 : 2);
+    if (strips_auto) strips = sms * (SRB == 32 ? 3 : 2);
     long long rps = (m + strips - 1) / strips;
     rps = (rps + SRB - 1) / SRB * SRB;
     t->rows_per_strip = rps;
@@ -903,13 +593,7 @@ int b200qr_tsqr_factor(b200qr_tsqr_t t, float *dA, long long ldm, float *dR, voi
             a.tau = t->d_stream_tau;
             a.Rout = t->strips > 1 ? t->slevels[0].stack : dR;        // the strips' triangles ARE the first level's stack
             a.ldr = t->strips > 1 ? (long long)t->strips * n : n;
-            if (t->wy) {
-                if (t->srb == 32) tsqr_strip_wy_kernel<32, 2, false><<<t->strips, n, 0, stream>>>(a);
-                else tsqr_strip_wy_kernel<48, 2, false><<<t->strips, n, 0, stream>>>(a);
-            } else if (t->early) {
-                if (t->srb == 32) tsqr_strip_early_kernel<32, 3, false><<<t->strips, n, 0, stream>>>(a);
-                else tsqr_strip_early_kernel<48, 2, false><<<t->strips, n, 0, stream>>>(a);
-            } else if (t->srb == 32) tsqr_strip_kernel<32, 3, false><<<t->strips, n, 0, stream>>>(a);
+            if (t->srb == 32) tsqr_strip_kernel<32, 3, false><<<t->strips, n, 0, stream>>>(a);
             else if (t->srb == 64) tsqr_strip_kernel<64, 2, false><<<t->strips, n, 0, stream>>>(a);
             else tsqr_strip_kernel<48, 2, false><<<t->strips, n, 0, stream>>>(a);
             CKB(cudaGetLastError());
@@ -927,9 +611,7 @@ int b200qr_tsqr_factor(b200qr_tsqr_t t, float *dA, long long ldm, float *dR, voi
             a.tau = L.tau;                                           // a.Rws: the first `pairs` triangles are reused
             a.Rout = pairs > 1 ? t->slevels[l + 1].stack : dR;
             a.ldr = pairs > 1 ? (long long)pairs * n : n;
-            if (t->wy) tsqr_strip_wy_kernel<TREE_RB, 2, true><<<pairs, n, 0, stream>>>(a);
-            else if (t->early) tsqr_strip_early_kernel<TREE_RB, 3, true><<<pairs, n, 0, stream>>>(a);
-            else tsqr_strip_kernel<TREE_RB, 3, true><<<pairs, n, 0, stream>>>(a);
+            tsqr_strip_kernel<TREE_RB, 3, true><<<pairs, n, 0, stream>>>(a);
             CKB(cudaGetLastError());
         }
         return B200QR_OK;

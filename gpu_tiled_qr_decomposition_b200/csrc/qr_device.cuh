@@ -244,39 +244,6 @@ __device__ __forceinline__ void bcast_col(float (&x)[TB], const float (&mine)[TB
     load_col_smem(x, slot);
 }
 
-// ------------------------------------------------------------------ a1: GEQRT ("QRS")
-// Householder QR of one 32x32 tile held by a warp, lane = column (reference semantics:
-// qrdecomp.c:532-557 SGEQRF, 1201-1227 calcvkSingle, 489-530 updateSingleQ_WY).
-// On exit a[] holds R on/above the diagonal and the reflector below it; the return value
-// of lane c is tau_c.  xs: 64 floats of shared-memory scratch (16-byte aligned).
-__device__ __forceinline__ float geqrt_warp(float (&a)[TB], float *xs, int lane)
-{
-    float my_tau = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < TB; ++c) {
-        float x[TB];
-        bcast_col(x, a, xs + (c & 1) * TB, lane == c);       // column c as it stands now
-        const float head = xs[(c & 1) * TB + c];
-        float v[TB];
-#pragma unroll
-        for (int r = 0; r < TB; ++r) v[r] = (r > c) ? x[r] : 0.f;
-        const HouseScalars h = house_scalars(head, dot32(v, v));
-        // v = [0 .. 0, 1, x_{c+1..}/piv]
-#pragma unroll
-        for (int r = 0; r < TB; ++r) v[r] = (r > c) ? v[r] * h.inv : ((r == c) ? 1.0f : 0.f);
-        // A(:, j) -= tau v (v' A(:, j)) for j >= c
-        const float f = (lane >= c) ? -h.tau * dot32(a, v) : 0.f;
-#pragma unroll
-        for (int r = 0; r < TB; ++r) a[r] = fmaf(f, v[r], a[r]);
-        if (lane == c) {
-#pragma unroll
-            for (int r = 0; r < TB; ++r) a[r] = (r > c) ? v[r] : a[r];
-            my_tau = h.tau;
-        }
-    }
-    return my_tau;
-}
-
 // ------------------------------------------------------------------ a2: TSQRT ("QRD")
 // QR of [R; B] with R upper triangular (kept in shared memory, Rs[row*33 + col]) and B a
 // full 32x32 tile held by the warp, lane = column (reference: qrdecomp.c:689-721 STSQRF,
@@ -295,19 +262,26 @@ __device__ __forceinline__ float tsqrt_warp_v(float (&b)[TB], float *Rs, float *
 {
     float my_tau = 0.f;
     float ssq = dot32(b, b);
-    float *vdst = SWZ ? reinterpret_cast<float *>(reinterpret_cast<char *>(vout) + (lane & 3) * 4)
-                      : vout + lane;
+    float *vdst = SWZ ? reinterpret_cast<float *>(reinterpret_cast<char *>(vout) + (lane & 3) * 4) : vout + lane;
 #pragma unroll 1
     for (int c = 0; c < TB; ++c) {
         if (c == 8) mid();
+        float *slot = xs + (c & 1) * TB;
+        if (lane == c) store_col_smem(slot, b);
+        const float ssq_c = __shfl_sync(FULL, ssq, c);
         const float rc = Rs[c * 33 + lane];                   // R(c, lane)
         const float diag = Rs[c * 33 + c];                    // R(c, c): broadcast read
-        float *slot = xs + (c & 1) * TB;
+        __syncwarp();
         float x[TB];
-        bcast_col(x, b, slot, lane == c);                     // x = B(:, c)
-        const HouseScalars h = house_scalars(diag, __shfl_sync(FULL, ssq, c));
+        load_col_smem(x, slot);                               // x = B(:, c)
+        const HouseScalars h = house_scalars(diag, ssq_c);
+        // Every lane forms the dot product, unconditionally: with no branch in the loop body the scheduler runs the
+        // rsqrt / rcp chain of the Householder scalars underneath the shared-memory broadcast and the dot product
+        // (round 1 had a lane >= c branch here: 15.3k cycles per tile, now 13.0k; tools/probe_panel.py).
+        float d = dot32(b, x);
+        asm volatile("" : "+f"(d));
         // beta = tau (R(c,j) + v' B(:,j)),  v = x / piv
-        const float beta = (lane >= c) ? h.tau * fmaf(h.inv, dot32(b, x), rc) : 0.f;
+        const float beta = (lane >= c) ? h.tau * fmaf(h.inv, d, rc) : 0.f;
         Rs[c * 33 + lane] = rc - beta;
         const float g = (lane > c) ? -beta * h.inv : 0.f;
 #pragma unroll
@@ -329,6 +303,95 @@ __device__ __forceinline__ float tsqrt_warp(float (&b)[TB], float *Rs, float *xs
     load_col_smem(b, vtmp + lane * TB);
     __syncwarp();
     return t;
+}
+
+// ------------------------------------------------------------------ a1: GEQRT ("QRS")
+// Householder QR of one 32x32 tile held by a warp, lane = column (reference semantics: qrdecomp.c:532-557 SGEQRF,
+// 1201-1227 calcvkSingle, 489-530 updateSingleQ_WY).  On exit a[] holds R on/above the diagonal and the reflector
+// below it; the return value of lane c is tau_c.  xs: 64 floats of shared-memory scratch (16-byte aligned).
+// Fully unrolled over the reflector index: every row mask (r > c) is a compile-time fact, so the passes
+// over a column shrink with c (16 rows on average instead of 32 with 96 selects per reflector), the dot product
+// runs against the UNSCALED column (its scale 1/piv goes onto the scalar, off the rsqrt / rcp chain, as in TSQRT)
+// and the sub-column sum of squares the next owner needs comes out of the update pass.  Measured (tools/
+// probe_panel.py): 9.9k cycles per tile against 30.9k for round 1's rolled loop with runtime masks.
+template <int C>
+__device__ __forceinline__ void geqrt_step(float (&a)[TB], float *xs, int lane, float &ssq_next, float &my_tau)
+{
+    float *slot = xs + (C & 1) * TB;
+    constexpr int R0 = C & ~3;                                // first 4-row chunk that holds a row >= C
+    if (lane == C) {
+#pragma unroll
+        for (int r = R0; r < TB; r += 4) *reinterpret_cast<float4 *>(slot + r) = make_float4(a[r], a[r + 1], a[r + 2], a[r + 3]);
+    }
+    const float ssq_c = __shfl_sync(FULL, ssq_next, C);
+    __syncwarp();
+    float x[TB];
+#pragma unroll
+    for (int r = R0; r < TB; r += 4) {
+        const float4 t = *reinterpret_cast<const float4 *>(slot + r);
+        x[r] = t.x; x[r + 1] = t.y; x[r + 2] = t.z; x[r + 3] = t.w;
+    }
+    const HouseScalars h = house_scalars(x[C], ssq_c);
+    // d = sum_{r > C} a[r] x[r]  (four partial sums)
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+    for (int r = C + 1; r < TB; ++r) {
+        const int s = (r - C - 1) & 3;
+        if (s == 0) d0 = fmaf(a[r], x[r], d0);
+        else if (s == 1) d1 = fmaf(a[r], x[r], d1);
+        else if (s == 2) d2 = fmaf(a[r], x[r], d2);
+        else d3 = fmaf(a[r], x[r], d3);
+    }
+    const float d = (d0 + d1) + (d2 + d3);
+    // A(:, j) -= tau v (v' A(:, j)),  v = [1; x / piv]:  f = tau (a_C + d / piv)
+    const float f = (lane >= C) ? h.tau * fmaf(h.inv, d, a[C]) : 0.f;
+    const float g = (lane > C) ? -f * h.inv : 0.f;
+    a[C] -= f;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int r = C + 1; r < TB; ++r) {
+        a[r] = fmaf(g, x[r], a[r]);
+        if (r > C + 1) {                                       // sum of squares below the NEXT diagonal (lane C + 1 uses it)
+            const int s = (r - C - 2) & 3;
+            if (s == 0) s0 = fmaf(a[r], a[r], s0);
+            else if (s == 1) s1 = fmaf(a[r], a[r], s1);
+            else if (s == 2) s2 = fmaf(a[r], a[r], s2);
+            else s3 = fmaf(a[r], a[r], s3);
+        }
+    }
+    ssq_next = (s0 + s1) + (s2 + s3);
+    if (lane == C) {                                           // the owner keeps the reflector (predicated: one lane)
+#pragma unroll
+        for (int r = C + 1; r < TB; ++r) a[r] = x[r] * h.inv;
+        my_tau = h.tau;
+    }
+}
+template <int C>
+__device__ __forceinline__ void geqrt_steps(float (&a)[TB], float *xs, int lane, float &ssq_next, float &my_tau)
+{
+    if constexpr (C < TB) {
+        geqrt_step<C>(a, xs, lane, ssq_next, my_tau);
+        geqrt_steps<C + 1>(a, xs, lane, ssq_next, my_tau);
+    }
+}
+__device__ __forceinline__ float geqrt_warp(float (&a)[TB], float *xs, int lane)
+{
+    float my_tau = 0.f;
+    float ssq = 0.f;                                           // sum_{r > 0} a[r]^2 (lane 0's is the one used)
+    {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int r = 1; r < TB; r += 4) {
+            s0 = fmaf(a[r], a[r], s0);
+            if (r + 1 < TB) s1 = fmaf(a[r + 1], a[r + 1], s1);
+            if (r + 2 < TB) s2 = fmaf(a[r + 2], a[r + 2], s2);
+            if (r + 3 < TB) s3 = fmaf(a[r + 3], a[r + 3], s3);
+        }
+        ssq = (s0 + s1) + (s2 + s3);
+    }
+    geqrt_steps<0>(a, xs, lane, ssq, my_tau);
+    __syncwarp();
+    return my_tau;
 }
 
 // ------------------------------------------------------------------ a3/a4: UNMQR / TSMQR

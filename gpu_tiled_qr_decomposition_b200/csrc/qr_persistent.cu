@@ -40,7 +40,9 @@
 namespace qrb200 {
 
 constexpr int CW = 8;                         // consumer warps per CTA
-constexpr int NPW = 2;                        // panel warps per CTA (one TSQRT chain each)
+constexpr int NPW = 2;                        // panel warps of a CTA that runs both roles (one TSQRT chain each)
+constexpr int NPW_SPLIT = 4;                  // panel warps of a panel-only CTA (role split): four chains share an SM at
+                                              // full speed, eight run at 0.65 of it each (tools/probe_panel.py)
 constexpr int NTHREADS = (CW + 2 + NPW) * 32; // + loader, storer, panel warps
 constexpr int SWEEP_THREADS = (CW + 2) * 32;  // threads that share a sweep ticket
 constexpr int W_LOADER = CW, W_STORER = CW + 1, W_PANEL = CW + 2;
@@ -65,7 +67,6 @@ struct Params {
     const int *panel_tab;     // panel ticket -> k (the steps whose panel column this rank owns)
     int npanels;
     int rank, world;
-    int la_enable;            // panel warps also update the next panel's column (look-ahead)
     const int *peer_prog[MAXW];     // progress words of every rank ([rank] = prog)
     const float *peer_tauc[MAXW];   // compact tau of every rank ([rank] = tauc)
     int *prog_w[MAXW];              // tensor-core engine 3: every rank's progress words, writable (the builder warps push them)
@@ -87,11 +88,11 @@ struct Cfg {
     // per panel warp: 2 input tiles, 1 output tile, R (33-float rows) + broadcast slots.  The NC = 2
     // variant only runs role-split (a CTA is either a panel CTA or a sweep CTA), so its panel region
     // overlays the sweep stages; NC = 1 keeps them apart and can run both roles in one CTA.
-    static constexpr int PANEL_BYTES = 8 * TILE_BYTES + 5120;      // in 2, out 2, R/scratch, top 1, look-ahead 3
+    static constexpr int PANEL_BYTES = 4 * TILE_BYTES + 5120;      // in 2, out 2, R / broadcast slots / tau
     static constexpr int OFF_PANEL = NC == 2 ? 0 : SWEEP_END;
     static constexpr int OFF_BAR = NC == 2 ? SWEEP_END : SWEEP_END + NPW * PANEL_BYTES;
     static constexpr int SMEM_BYTES = OFF_BAR + 256;
-    static constexpr bool BUILD_T = false;            // panel warps also emit the compact-WY T factors (tensor-core engine 3)
+    static_assert(NC != 2 || NPW_SPLIT * PANEL_BYTES <= SWEEP_END, "panel region of a panel-only CTA");
 };
 
 // The CTA's dynamic shared memory (no static __shared__ in this kernel, so it starts at offset 0
@@ -131,11 +132,19 @@ __device__ __forceinline__ unsigned long long gtimer()
     return t;
 }
 
+// The limit is on the time ONE wait has been spinning without success (a wait that never ends = a scheduler bug), not
+// on the kernel's run time: every waiting loop owns a Spin, whose clock starts at its first check (16384 polls in), so a
+// long factorisation under throttled clocks, a sanitizer or a profiler is not killed as long as it keeps moving.
+struct Spin { unsigned n = 0; unsigned long long since = 0; };
 struct Watch {
     unsigned long long t0, limit;
-    __device__ __forceinline__ void check(unsigned &spins) const
+    __device__ __forceinline__ void check(Spin &s) const
     {
-        if (((++spins) & 0x3fffu) == 0 && gtimer() - t0 > limit) __trap();
+        if (((++s.n) & 0x3fffu) == 0) {
+            const unsigned long long now = gtimer();
+            if (s.since == 0) s.since = now;
+            else if (now - s.since > limit) __trap();
+        }
     }
 };
 
@@ -143,13 +152,13 @@ struct Watch {
 // the kernel (host sees a launch failure -> B200QR_ESTALL).
 __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, const Watch &w)
 {
-    unsigned spins = 0;
+    Spin spins;
     while (!mbar_try_wait(bar, parity)) w.check(spins);
 }
 // Spin (whole warp, one coalesced L2 load per iteration) until *p >= target, then acquire.
 __device__ __forceinline__ void wait_flag(const int *p, int target, const Watch &w)
 {
-    unsigned spins = 0;
+    Spin spins;
     while (ld_relaxed(p) < target) { __nanosleep(32); w.check(spins); }
     __threadfence();
 }
@@ -170,21 +179,13 @@ __device__ __forceinline__ void trace_mark(const Params &P, int k, int i, int j,
             P.trace_mode == 2 ? (int)(unsigned)gtimer() : atomicAdd(&P.ctr[1], 1);
 }
 
-// Look-ahead: the panel warp of step k also applies the step to tile column k+1 -- the next panel's
-// column -- tile by tile right behind its own TSQRT, with the reflector block still in shared
-// memory.  The next panel then depends on this warp only (not on a sweep CTA's load / compute /
-// store / publish round trip), which shortens the lag between consecutive panels from ~75 us to
-// ~35 us; the sweeps skip that column.  Not done across a distribution-block boundary with several
-// ranks (column k+1 then lives on another GPU): there the ordinary sweep keeps the column.
-__device__ __forceinline__ bool lookahead(const Params &P, int k, int G)
-{
-    return P.la_enable && k + 1 < P.q && (P.world == 1 || (k + 1) % G != 0);
-}
-
 // ------------------------------------------------------------------ P(k): the panel warp
+// (Round 1 had an optional look-ahead here -- the panel warp also applied its block to tile column k+1.  Measured in round
+// 2 with the device trace (tools/trace_timeline.py, 8192^2): it lengthens the chain from 10.6 to 14.3 us per tile and the
+// lag between consecutive panel starts from 43 to 50 us, because it serialises in one warp what the sweep CTA does
+// concurrently with the next TSQRT.  Removed; what shortens the lag is a shorter GEQRT / TSQRT.)
 template <int NC>
-__device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int pw, uint32_t &phbits, const Watch &wd,
-                          const CUtensorMap *mapW = nullptr, int wcols = 0)
+__device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int pw, uint32_t &phbits, const Watch &wd)
 {
     using C = Cfg<NC>;
     const int lane = threadIdx.x & 31;
@@ -194,35 +195,21 @@ __device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int p
     float *pout0 = reinterpret_cast<float *>(mine + 2 * TILE_BYTES);   // 2 output slots (tile row parity)
     float *Rs = reinterpret_cast<float *>(mine + 4 * TILE_BYTES);
     float *xs = reinterpret_cast<float *>(mine + 4 * TILE_BYTES + 4352);   // 2 x 128 B broadcast slots
-    float *ptau = reinterpret_cast<float *>(mine + 4 * TILE_BYTES + 4608); // tau of the current block
-    float *ptop = reinterpret_cast<float *>(mine + 4 * TILE_BYTES + 5120); // look-ahead: tile (k, k+1), [c][lane]
-    float *pla0 = reinterpret_cast<float *>(mine + 5 * TILE_BYTES + 5120); // look-ahead: 3 in/out slots
-    // BUILD_T (no look-ahead there): the slots behind the broadcast area stage the six operand tiles and the Gram
-    // scratch of build_t_warp (PANEL_BYTES of that configuration has room for seven tiles there)
-    float *opstage = ptop, *gscratch = ptop + 6 * TB * TB;
-    auto store_ops = [&](int row) {                  // lane 0: the six operand tiles -> workspace columns k*192 ..
-        tma_store_2d(mapW, row * TB, k * 6 * TB, opstage);       // one box: the six tiles are adjacent in the stage and in the workspace
-    };
     uint64_t *pfull = reinterpret_cast<uint64_t *>(g_smem + C::OFF_BAR) + 3 * C::NS + 2 * pw;
     int *prog_col = P.prog + (size_t)k * p;
-    int *prog_la = P.prog + (size_t)(k + 1) * p;
     float *tauc = P.tauc + (size_t)k * p * TB;
-    const bool la = lookahead(P, k, C::G);
 
-    auto ready = [&](int row) {
-        return ld_relaxed(prog_col + row) >= k && (!la || ld_relaxed(prog_la + row) >= k);
-    };
+    auto ready = [&](int row) { return ld_relaxed(prog_col + row) >= k; };
     auto wait_ready = [&](int row) {
-        unsigned spins = 0;
+        Spin spins;
         while (!ready(row)) { __nanosleep(32); wd.check(spins); }
         __threadfence();
     };
-    auto issue = [&](int row, int s) {               // TMA-load tile (row, k) [and (row, k+1)] into slot s
+    auto issue = [&](int row, int s) {               // TMA-load tile (row, k) into slot s
         if (lane == 0) {
             fence_proxy_async();
-            mbar_arrive_expect_tx(&pfull[s], la ? 2 * TILE_BYTES : TILE_BYTES);
+            mbar_arrive_expect_tx(&pfull[s], TILE_BYTES);
             tma_load_2d(pin0 + s * TB * TB, mapA, row * TB, k * TB, &pfull[s]);
-            if (la) tma_load_2d(pla0 + ((row - k) % 3) * TB * TB, mapA, row * TB, (k + 1) * TB, &pfull[s]);
         }
     };
     int pending = -1;                                // tile row whose stores are in flight, unpublished
@@ -236,10 +223,6 @@ __device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int p
                 bulk_wait_all();
                 __threadfence();
                 st_release(prog_col + pending, k + 1);
-                if (la && pending > k) {
-                    trace_mark(P, k, pending, k + 1, 1);
-                    st_release(prog_la + pending, k + 1);
-                }
             }
             pending = -1;
         }
@@ -260,28 +243,13 @@ __device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int p
     {
         float *pout = pout0 + (k & 1) * TB * TB;
         store_col_sw(pout, lane, a);
-        ptau[lane] = t;
-        if (C::BUILD_T) {
-            __syncwarp();
-            build_t_warp<true>(pout, t, gscratch, opstage, lane);
-        }
         fence_proxy_async_smem();
         __syncwarp();                                // also orders this warp's tau stores before lane 0's release
         if (lane == 0) {
             tma_store_2d(mapA, k * TB, k * TB, pout);
-            if (C::BUILD_T) store_ops(k);
             bulk_commit();
         }
         pending = k;
-        if (la) {                                    // UNMQR on tile (k, k+1): it stays in shared memory (ptop)
-            float x[TB];
-            load_col_sw(x, pla0, lane);
-            if (lane == 0) trace_mark(P, k, k, k + 1, 0);
-            apply_reflectors_nc<1, false, true>(x, x, nullptr, nullptr, 0, pout, ptau);
-#pragma unroll
-            for (int r = 0; r < TB; ++r) ptop[r * TB + lane] = x[r];
-            if (lane == 0) trace_mark(P, k, k, k + 1, 1);
-        }
     }
 
     // ---- TSQRT chain down the tile column; R stays in shared memory
@@ -306,52 +274,28 @@ __device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int p
         if (lane == 0) trace_mark(P, k, i, k, 1);
         publish();
         tauc[i * TB + lane] = ti;
-        if (C::BUILD_T) {
-            __syncwarp();                            // lane 0 has waited for the previous tile's stores: the stages are free
-            build_t_warp<false>(pout, ti, gscratch, opstage, lane);
-        }
-        float *pla = pla0 + ((i - k) % 3) * TB * TB;
-        if (la) {                                    // TSMQR on [ptop; tile (i, k+1)] with the block just built
-            ptau[lane] = ti;
-            __syncwarp();
-            float x[TB];
-            load_col_sw(x, pla, lane);
-            if (lane == 0) trace_mark(P, k, i, k + 1, 0);
-            apply_reflectors_nc<1, true, true>(x, x, ptop + lane, ptop + lane, TB, pout, ptau);
-            store_col_sw(pla, lane, x);
-        }
         fence_proxy_async_smem();
         __syncwarp();                                // also orders this warp's tau stores before lane 0's release
         if (lane == 0) {
             tma_store_2d(mapA, i * TB, k * TB, pout);
-            if (la) tma_store_2d(mapA, i * TB, (k + 1) * TB, pla);
-            if (C::BUILD_T) store_ops(i);
             bulk_commit();
         }
         pending = i;
         have_cur = have_next;
     }
     publish();
-    // ---- final diagonal tile: R from the chain above the diagonal, GEQRT reflectors below;
-    //      and the resident tile (k, k+1) of the look-ahead column
+    // ---- final diagonal tile: R from the chain above the diagonal, GEQRT reflectors below
     float f[TB];
 #pragma unroll
     for (int r = 0; r < TB; ++r) f[r] = Rs[r * 33 + lane];
     store_col_sw(pout0, lane, f);
-    if (la) {
-#pragma unroll
-        for (int r = 0; r < TB; ++r) f[r] = ptop[r * TB + lane];
-        store_col_sw(pla0, lane, f);
-    }
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
         tma_store_2d(mapA, k * TB, k * TB, pout0);
-        if (la) tma_store_2d(mapA, k * TB, (k + 1) * TB, pla0);
         bulk_commit();
         bulk_wait_all();
         __threadfence();
-        if (la) st_release(prog_la + k, k + 1);
         // "tile column k is final": the diagonal word moves on to k + 2 once the last store of the panel has landed
         // (every reader of this word asks for >= k + 1).  The host uses it to copy finished columns back while the
         // kernel is still running (cudaQRTask).
@@ -387,8 +331,7 @@ __device__ void sweep_loader(const Params &P, const CUtensorMap *mapA, const CUt
     const int lane = threadIdx.x & 31;
     const int p = P.p, nrows = p - k;
     const int jt = g * C::G + lane;                              // lanes 0..G-1: one tile column each
-    const int kla = k + (lookahead(P, k, C::G) ? 1 : 0);         // the panel warp keeps column k+1 itself
-    const bool active = lane < C::G && jt > kla && jt < P.q;
+    const bool active = lane < C::G && jt > k && jt < P.q;
     const unsigned amask = __ballot_sync(FULL, active);
     const uint32_t bytes = __popc(amask) * TILE_BYTES + TILE_BYTES + 128;
     const int owner = (k / C::G) % P.world;                      // rank holding the panel column of step k
@@ -404,7 +347,7 @@ __device__ void sweep_loader(const Params &P, const CUtensorMap *mapA, const CUt
         mbar_wait_wd(cx.empty(s), ring.phase ^ 1, wd);
         if (idx < nrows) {
             const int row = k + idx;
-            unsigned spins = 0;
+            Spin spins;
             for (;;) {
                 bool ok = flag ? (flag_remote ? ld_relaxed_sys(flag + row) : ld_relaxed(flag + row)) >= target : true;
                 if (__all_sync(FULL, ok)) break;
@@ -433,8 +376,7 @@ __device__ void sweep_storer(const Params &P, const CUtensorMap *mapA, int k, in
     const int lane = threadIdx.x & 31;
     const int p = P.p, nrows = p - k;
     const int jt = g * C::G + lane;
-    const int kla = k + (lookahead(P, k, C::G) ? 1 : 0);
-    const bool active = lane < C::G && jt > kla && jt < P.q;
+    const bool active = lane < C::G && jt > k && jt < P.q;
 
     for (int idx = 0; idx <= nrows; ++idx) {
         const int s = ring.stage;
@@ -469,7 +411,7 @@ __device__ void sweep_consumer(const Params &P, int k, int g, const SweepCtx<NC>
 #pragma unroll
     for (int n = 0; n < NC; ++n) {
         jts[n] = g * C::G + n * CW + w;
-        act[n] = jts[n] > k + (lookahead(P, k, C::G) ? 1 : 0) && jts[n] < P.q;
+        act[n] = jts[n] > k && jts[n] < P.q;
     }
 
     for (int idx = 0; idx <= nrows; ++idx) {
@@ -536,7 +478,7 @@ tiledqr_persistent(const __grid_constant__ KernelArgs KA)
     const CUtensorMap *mapVs = KA.rc[vr].mapV;
     uint64_t *bars = reinterpret_cast<uint64_t *>(g_smem + C::OFF_BAR);
     uint64_t *full = bars, *computed = bars + C::NS, *empty = bars + 2 * C::NS, *pfull = bars + 3 * C::NS;
-    int *s_task = reinterpret_cast<int *>(bars + 3 * C::NS + 2 * NPW);
+    int *s_task = reinterpret_cast<int *>(bars + 3 * C::NS + 2 * NPW_SPLIT);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const Watch wd{gtimer(), P.watchdog_ns};
     const bool split = P.npanel_ctas > 0;
@@ -549,26 +491,27 @@ tiledqr_persistent(const __grid_constant__ KernelArgs KA)
             mbar_init(&computed[s], CW * 32);
             mbar_init(&empty[s], 1);
         }
-        for (int i = 0; i < 2 * NPW; ++i) mbar_init(&pfull[i], 1);
+        for (int i = 0; i < 2 * NPW_SPLIT; ++i) mbar_init(&pfull[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tma_prefetch_desc(&mapA);
         for (int r = 0; r < P.world; ++r) tma_prefetch_desc(&mapVs[r]);
     }
     __syncthreads();
 
-    if (warp >= W_PANEL) {
-        if (!panel_cta) return;
+    // panel warps: the last NPW warps of a CTA that runs both roles; the first NPW_SPLIT warps of a panel-only CTA
+    const int pw = split ? (panel_cta && warp < NPW_SPLIT ? warp : -1) : (warp >= W_PANEL ? warp - W_PANEL : -1);
+    if (pw >= 0) {
         uint32_t phbits = 0;
         for (;;) {
             int t = 0;
             if (lane == 0) t = atomicAdd(&P.ctr[2], 1);
             t = __shfl_sync(FULL, t, 0);
             if (t >= P.npanels) break;
-            run_panel<NC>(P, &mapA, P.panel_tab[t], warp - W_PANEL, phbits, wd);
+            run_panel<NC>(P, &mapA, P.panel_tab[t], pw, phbits, wd);
         }
         return;
     }
-    if (!sweep_cta) return;
+    if (!sweep_cta || warp >= W_PANEL) return;
 
     SweepCtx<NC> cx;
     Ring ring;
@@ -582,11 +525,7 @@ tiledqr_persistent(const __grid_constant__ KernelArgs KA)
         named_bar_sync(1, SWEEP_THREADS);
         const int k = s_task[0], g = s_task[1];
         if (k < 0) break;
-        {   // a diagonal-group sweep whose only column went to the look-ahead has nothing to do
-            const int j_lo = max(g * C::G, k + 1 + (lookahead(P, k, C::G) ? 1 : 0));
-            const int j_hi = min((g + 1) * C::G, P.q);
-            if (j_lo >= j_hi) continue;
-        }
+        if (max(g * C::G, k + 1) >= min((g + 1) * C::G, P.q)) continue;
         if (warp == W_LOADER) sweep_loader<NC>(P, &mapA, mapVs, k, g, cx, ring, wd);
         else if (warp == W_STORER) sweep_storer<NC>(P, &mapA, k, g, cx, ring, wd);
         else sweep_consumer<NC>(P, k, g, cx, ring, wd);
@@ -594,8 +533,6 @@ tiledqr_persistent(const __grid_constant__ KernelArgs KA)
 }
 
 }  // namespace qrb200
-#include "qr_persistent_tc.cuh"
-#include "qr_persistent_tc2.cuh"
 #include "qr_persistent_tc3.cuh"
 namespace qrb200 {
 
@@ -755,7 +692,6 @@ struct b200qr_plan_s {
     int npanel_ctas;        // role split (0 = every CTA runs both roles)
     int nsweeps, npanels;   // tickets of this rank
     int rank = 0, world = 1;
-    int la_enable = 0;
     float *peer_A[MAXW];
     int *peer_prog[MAXW];
     float *peer_tauc[MAXW];
@@ -805,22 +741,18 @@ static int make_tile_map(CUtensorMap *map, float *dA, int m, int n, int ldm, boo
     return r == CUDA_SUCCESS ? B200QR_OK : B200QR_ECUDA;
 }
 
-// kernel variants: 1 / 2 = SIMT sweeps with 1 / 2 matrix columns per consumer thread, 3 / 4 / 5 = tensor-core sweeps
+// kernel variants: 1 / 2 = SIMT sweeps with 1 / 2 matrix columns per consumer thread, 5 = tensor-core sweeps
+// (3 and 4 were the two earlier tensor-core engines of round 1, removed)
 static const void *kernel_of(int nc, bool prof = false)
 {
     if (nc == 5) return prof ? (const void *)tiledqr_persistent_tc3_prof : (const void *)tiledqr_persistent_tc3;
-    return nc == 4 ? (const void *)tiledqr_persistent_tc2
-                   : (nc == 3 ? (const void *)tiledqr_persistent_tc
-                              : (nc == 2 ? (const void *)tiledqr_persistent<2> : (const void *)tiledqr_persistent<1>));
+    return nc == 2 ? (const void *)tiledqr_persistent<2> : (const void *)tiledqr_persistent<1>;
 }
-static int smem_of(int nc)
-{
-    if (nc == 5) return Cfg<5>::SMEM_BYTES;
-    return nc == 4 ? Cfg<4>::SMEM_BYTES : (nc == 3 ? Cfg<3>::SMEM_BYTES : (nc == 2 ? Cfg<2>::SMEM_BYTES : Cfg<1>::SMEM_BYTES));
-}
-static int threads_of(int nc) { return nc == 5 ? tc3::NTHREADS_TC3 : nc == 4 ? tc2::NTHREADS_TC2 : (nc == 3 ? tc::NTHREADS_TC : NTHREADS); }
-static int group_of(int nc) { return nc == 5 ? Cfg<5>::G : nc == 4 ? Cfg<4>::G : (nc == 3 ? Cfg<3>::G : CW * nc); }
-constexpr int CTR_INTS = 64 + 512;     // tickets / trace / SM claim words of the 2-CTA-per-SM engine
+static int smem_of(int nc) { return nc == 5 ? Cfg<5>::SMEM_BYTES : (nc == 2 ? Cfg<2>::SMEM_BYTES : Cfg<1>::SMEM_BYTES); }
+static int threads_of(int nc) { return nc == 5 ? tc3::NTHREADS_TC3 : NTHREADS; }
+static int group_of(int nc) { return nc == 5 ? Cfg<5>::G : CW * nc; }
+constexpr int CTR_INTS = 64 + 512;     // tickets / trace sequence / phase timers
+constexpr int TC_AUTO_MIN_K = 384;     // automatic engine choice: tensor-core sweeps from this many steps on
 
 extern "C" {
 
@@ -874,37 +806,42 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
     int dev = 0, sms = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    for (int nc = 1; nc <= 5; ++nc) {
+    for (int nc : {1, 2, 5}) {
         CK(cudaFuncSetAttribute(kernel_of(nc), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(nc)));
         CK(cudaFuncSetAttribute(kernel_of(nc), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     }
     CK(cudaFuncSetAttribute(kernel_of(5, true), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_of(5)));
     CK(cudaFuncSetAttribute(kernel_of(5, true), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel_of(3), threads_of(3), smem_of(3)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel_of(5), threads_of(5), smem_of(5)));
     if (occ < 1) return B200QR_EINVAL;
     int grid = occ * sms / nvirt;                  // every CTA must be co-resident (cooperative launch)
     if (opts && opts->grid_ctas > 0 && opts->grid_ctas < grid) grid = opts->grid_ctas;
 
     // Kernel variant and roles.  Large grids split the roles: a few CTAs run only TSQRT chains
-    // (two panel warps each, undisturbed by the FFMA-bound consumers), the rest only sweeps with
-    // 2 matrix columns per consumer thread (16 tile columns per sweep).  The number of panel CTAs
-    // balances the two streams with the costs measured on a B200 (tools/probe_panel.py,
-    // tools/trace_timeline.py): 8.7 us per TSQRT of a chain, 0.54 us of sweep-CTA time per trailing
-    // tile task.  The panel chains of consecutive steps live on ONE rank at a time (a block of 16
-    // tile columns), so the panel stream does not speed up with more ranks while each rank's sweep
-    // share shrinks: the split is world-aware.  Small grids (tests, tiny matrices) run both roles
-    // in every CTA with the 1-column variant.  With several ranks the variant must be the same
-    // everywhere (it fixes the distribution block), so it depends on shape and world size only.
+    // (panel warps undisturbed by the FFMA-bound consumers), the rest only sweeps.  Small grids
+    // (tests, tiny matrices) run both roles in every CTA with the 1-column SIMT variant.
+    // The ENGINE is a pure function of (m, n, world) and the caller's explicit choice
+    // (opts.engine, or QRB200_TC=0 / 3 in the environment when opts.engine is 0) -- never of what
+    // happens to be free on the device: with several ranks it fixes the distribution block, so
+    // every rank must arrive at the same answer (b200qr_dist_connect checks it), and a result
+    // must not change its rounding with the memory pressure of the day.  If the tensor-core
+    // engine's operand workspace does not fit, plan creation fails with B200QR_ENOMEM.
     pl->nc = 1; pl->npanel_ctas = 0;
     const bool big = world > 1 ? q >= 32 * world : (grid >= 16 && q >= 32);
+    int engine = opts ? opts->engine : 0;
+    if (engine < 0 || engine > 2) return B200QR_EINVAL;
+    if (engine == 0) {
+        const char *e = getenv("QRB200_TC");
+        if (e && *e) engine = atoi(e) != 0 ? 2 : 1;
+    }
     if (big && grid >= 16) {
         pl->nc = 2;
         double ptiles = 0, stiles = 0;
         for (int k = 0; k < K; ++k) { ptiles += p - k; stiles += (double)(p - k) * (q - k - 1); }
         int want = 2;
         for (; want < grid / 4; ++want) {
-            const double t_panel = ptiles * 8.7 / (NPW * want);
+            const double t_panel = ptiles * 7.2 / (NPW_SPLIT * want);
             const double t_sweep = stiles * 0.54 / ((double)world * (grid - want));
             if (t_panel <= 0.4 * t_sweep) break;
         }
@@ -919,41 +856,24 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
     } else if (pl->nc == 2 && grid < 16) {
         return B200QR_EINVAL;                      // cannot honour the world-wide variant on this grid
     }
-    // Tensor-core sweeps.  QRB200_TC = 1 / 2 / 3 forces one of the three engines (1, 2: earlier designs kept for
-    // comparison), QRB200_TC = 0 forces the SIMT engine.  Unset: engine 3 on one GPU once the matrix is large enough for
-    // its faster tile rows to outweigh its slower panel chain (measured on B200: 8192^2 SIMT 25.5 ms / engine 3 29.3 ms,
-    // 16384^2 178 / 149 ms, 32768^2 1358 / 1168 ms) and its operand workspace (six times the factored columns) fits.
-    if (pl->nc == 2) {
-        const char *e = getenv("QRB200_TC");
-        if (e && *e) {
-            const int tcv = atoi(e);
-            if (tcv != 0) pl->nc = (tcv == 3 && nvirt == 1) || (tcv == 2 && world == 1 && nvirt == 1) ? tcv + 2 : 3;
-        } else if (nvirt == 1 && K >= 384 && (world == 1 || q >= 32 * world)) {
-            // take the workspace now: if it does not fit (or the allocation fails), the SIMT engine runs instead
-            size_t free_b = 0, total_b = 0;
-            const size_t wbytes = sizeof(float) * (size_t)m * K * TB * 6;
-            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > wbytes + ((size_t)1 << 30)) {
-                if (cudaMalloc(&pl->d_W, wbytes) == cudaSuccess) pl->nc = 5;
-                else { pl->d_W = nullptr; (void)cudaGetLastError(); }
-            }
-        }
-    }
-    if (pl->nc >= 4) {
-        // one CTA per SM holding two sweep engines; a panel CTA runs four panel warps
-        int want = (pl->npanel_ctas * NPW + tc2::NPW4 - 1) / tc2::NPW4;
+    // Tensor-core sweeps (engine 2): explicit, or automatic once the matrix is large enough for their faster tile
+    // rows to outweigh the four-column sweep granularity (measured on B200, round 1: 8192^2 SIMT 25.5 ms / tensor
+    // 26.5 ms, 16384^2 178 / 131 ms, 32768^2 1358 / 950 ms).
+    if (pl->nc == 2 && (engine == 2 || (engine == 0 && K >= TC_AUTO_MIN_K && (world == 1 || q >= 32 * world)))) pl->nc = 5;
+    if (engine == 2 && pl->nc != 5) return B200QR_EINVAL;          // the grid / shape cannot run the tensor-core engine
+    if (pl->nc == 5) {
+        // one sweep engine per CTA and SM; a panel CTA runs NPW5 factor / builder warp pairs
+        int want = (pl->npanel_ctas * NPW_SPLIT + tc3::NPW5 - 1) / tc3::NPW5;
         if (const char *e = getenv("QRB200_NP")) { int v = *e ? atoi(e) : -1; if (v > 0 && v < grid) want = v; }
         pl->npanel_ctas = want < 1 ? 1 : want;
     }
     const int G = group_of(pl->nc);
     pl->G = G;
-    pl->la_enable = 0;
-    if (const char *e = getenv("QRB200_LOOKAHEAD")) pl->la_enable = atoi(e) != 0 && pl->nc != 5;
-    if (pl->nc == 5 && getenv("QRB200_SYSFENCE")) pl->la_enable = 2;      // engine 3 has no look-ahead: the field carries this experiment flag
 
     // this rank's tickets: sweeps of its blocks in the global skewed order, panels of its tile columns
     // skew of the sweep order: a tensor-core sweep row is several times faster than a TSQRT of the panel
     // chain, so its panel needs a longer head start than one distribution block of steps
-    int skew = pl->nc >= 4 ? 32 : G;
+    int skew = pl->nc == 5 ? 32 : G;
     if (const char *e = getenv("QRB200_SKEW")) { int v = atoi(e); if (v > 0) skew = v; }
     long npan = 0;
     long ns = b200qr_sched_rank_tickets_skew(p, q, G, skew, rank, world, nullptr, 0, nullptr, 0, &npan);
@@ -983,8 +903,8 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
     pl->nsweeps = (int)ns;
     pl->npanels = (int)npan;
     const int useful = (pl->nsweeps > pl->npanels ? pl->nsweeps : pl->npanels) + pl->npanel_ctas;
-    if (pl->nc < 4 && grid > useful) grid = useful > 0 ? useful : 1;
-    if (pl->nc < 4 && pl->npanel_ctas >= grid) pl->npanel_ctas = grid > 1 ? grid / 2 : 0;
+    if (pl->nc != 5 && grid > useful) grid = useful > 0 ? useful : 1;
+    if (pl->nc != 5 && pl->npanel_ctas >= grid) pl->npanel_ctas = grid > 1 ? grid / 2 : 0;
     if (pl->npanel_ctas == 0) {
         if (pl->nc == 2 && world > 1) return B200QR_EINVAL;
         pl->nc = 1;
@@ -1000,9 +920,9 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
     CK(cudaMalloc(&pl->d_tauc, sizeof(float) * (size_t)K * p * TB));
     CK(cudaMemset(pl->d_tauc, 0, sizeof(float) * (size_t)K * p * TB));
     CK(cudaMemset(pl->d_prog, 0, sizeof(int) * (size_t)p * q));
-    if (pl->nc == 5 && !pl->d_W) {
+    if (pl->nc == 5) {
         const size_t wbytes = sizeof(float) * (size_t)m * K * TB * 6;
-        if (cudaMalloc(&pl->d_W, wbytes) != cudaSuccess) return B200QR_ENOMEM;
+        if (cudaMalloc(&pl->d_W, wbytes) != cudaSuccess) { pl->d_W = nullptr; (void)cudaGetLastError(); return B200QR_ENOMEM; }
     }
     if (pl->trace && pl->trace != 3) {
         CK(cudaMalloc(&pl->d_trace, sizeof(int) * 2 * (size_t)tiles));
@@ -1030,7 +950,7 @@ static int fill_rank_ctx(RankCtx *rc, b200qr_plan_s *pl, float *dA, int ldm)
     P.tauc = pl->d_tauc; P.prog = pl->d_prog; P.ctr = pl->d_ctr;
     P.sweep_tab = pl->d_sweep_tab; P.nsweeps = pl->nsweeps; P.npanel_ctas = pl->npanel_ctas;
     P.panel_tab = pl->d_panel_tab; P.npanels = pl->npanels;
-    P.rank = pl->rank; P.world = pl->world; P.la_enable = pl->la_enable;
+    P.rank = pl->rank; P.world = pl->world;
     P.trace = (pl->trace && pl->trace != 3) ? pl->d_trace : nullptr; P.trace_off = pl->d_trace_off; P.trace_mode = pl->trace;
     if (getenv("QRB200_ONE_ENGINE")) P.trace_mode = 7;
     P.watchdog_ns = pl->watchdog_ns;
@@ -1040,7 +960,7 @@ static int fill_rank_ctx(RankCtx *rc, b200qr_plan_s *pl, float *dA, int ldm)
         float *src = r == pl->rank ? dA : pl->peer_A[r];
         int ld = r == pl->rank ? ldm : pl->m;
         if (!src) return B200QR_EINVAL;            // peers not connected
-        rc_ = make_tile_map(&rc->mapV[r], src, pl->m, pl->n, ld, pl->nc >= 3);   // tensor-core operands are swizzled
+        rc_ = make_tile_map(&rc->mapV[r], src, pl->m, pl->n, ld, pl->nc == 5);   // tensor-core operands are swizzled
     }
     if (pl->nc == 5 && rc_ == B200QR_OK) {
         rc_ = make_tile_map(&rc->mapW, pl->d_W, pl->m, 6 * pl->K * TB, pl->m, true, 6 * TB);
@@ -1134,7 +1054,9 @@ struct b200qr_dist_s {
     int connected = 0;
 };
 
-struct ipc_blob { cudaIpcMemHandle_t a, prog, tauc, w; int has_w; };
+// what a rank tells the others: its buffers, and the plan facts every rank must agree on (the kernel variant fixes the
+// distribution block, so ranks with different variants would disagree on who owns which tile column)
+struct ipc_blob { cudaIpcMemHandle_t a, prog, tauc, w; int has_w, nc, G, m, n, world, rank; };
 
 int b200qr_dist_handle_bytes(void) { return (int)sizeof(ipc_blob); }
 
@@ -1184,6 +1106,7 @@ int b200qr_dist_export(b200qr_dist_t d, void *out_bytes)
     memset(&b.w, 0, sizeof b.w);
     b.has_w = d->plan.d_W != nullptr;
     if (b.has_w) CK(cudaIpcGetMemHandle(&b.w, d->plan.d_W));
+    b.nc = d->plan.nc; b.G = d->plan.G; b.m = d->plan.m; b.n = d->plan.n; b.world = d->plan.world; b.rank = d->plan.rank;
     memcpy(out_bytes, &b, sizeof b);
     return B200QR_OK;
 }
@@ -1193,6 +1116,10 @@ int b200qr_dist_connect(b200qr_dist_t d, const void *all_bytes)
     if (!d || !all_bytes) return B200QR_EINVAL;
     const ipc_blob *blobs = (const ipc_blob *)all_bytes;
     b200qr_plan_s &pl = d->plan;
+    for (int r = 0; r < pl.world; ++r)                                // every rank made the same plan, or nobody connects
+        if (blobs[r].nc != pl.nc || blobs[r].G != pl.G || blobs[r].m != pl.m || blobs[r].n != pl.n || blobs[r].world != pl.world ||
+            blobs[r].rank != r || (pl.nc == 5 && !blobs[r].has_w))
+            return B200QR_EINVAL;
     for (int r = 0; r < pl.world; ++r) {
         if (r == pl.rank) continue;
         void *a = nullptr, *pr = nullptr, *tc = nullptr;
@@ -1201,8 +1128,7 @@ int b200qr_dist_connect(b200qr_dist_t d, const void *all_bytes)
         CK(cudaIpcOpenMemHandle(&tc, blobs[r].tauc, cudaIpcMemLazyEnablePeerAccess));
         d->opened[4 * r] = a; d->opened[4 * r + 1] = pr; d->opened[4 * r + 2] = tc;
         pl.peer_A[r] = (float *)a; pl.peer_prog[r] = (int *)pr; pl.peer_tauc[r] = (float *)tc;
-        if (pl.nc == 5) {                                             // every rank must have made the same choice
-            if (!blobs[r].has_w) return B200QR_EINVAL;
+        if (pl.nc == 5) {
             void *w = nullptr;
             CK(cudaIpcOpenMemHandle(&w, blobs[r].w, cudaIpcMemLazyEnablePeerAccess));
             d->opened[4 * r + 3] = w;
@@ -1233,10 +1159,16 @@ int b200qr_dist_connect_local(b200qr_dist_t *all, int world)
 
 // Zero this rank's progress words / ticket counters.  Every rank must have done this (and the
 // ranks must have synchronised, e.g. a torch.distributed barrier) before any rank launches.
+// SYNCHRONOUS: returns once the words ARE zero on the device, so that a host barrier taken right
+// after it really means "every rank's words are reset" (a peer that launched first would otherwise
+// read this rank's final words of the previous factorisation).
 int b200qr_dist_reset(b200qr_dist_t d, void *stream)
 {
     if (!d) return B200QR_EINVAL;
-    return reset_progress(&d->plan, (cudaStream_t)stream);
+    int rc = reset_progress(&d->plan, (cudaStream_t)stream);
+    if (rc != B200QR_OK) return rc;
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return B200QR_OK;
 }
 
 // Launch this rank's persistent kernel (asynchronous).  The kernels of all ranks run at the same

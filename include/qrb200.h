@@ -37,7 +37,8 @@ enum {
     B200QR_EINVAL = -1,      /* bad shape / pointer / option                       */
     B200QR_ECUDA = -2,       /* a CUDA runtime call failed (b200qr_last_cuda_error) */
     B200QR_ENOMEM = -3,
-    B200QR_ESTALL = -4       /* persistent scheduler watchdog saw no progress       */
+    B200QR_ESTALL = -4       /* a wait inside the persistent kernel made no progress for QRB200_WATCHDOG_MS
+                                (default 60 000): the kernel trapped; reported by the synchronous entry points */
 };
 
 /* Task vocabulary of the reference (include/gridscheduler.h:10-17). */
@@ -57,7 +58,11 @@ typedef struct {
                            2 = record %globaltimer nanoseconds (low 32 bits) instead            */
     int share_device;   /* b200qr_dist_create only: number of rank objects that will share this device
                            and be launched together with b200qr_dist_factor_group (0/1 = none)    */
-    int reserved[5];
+    int engine;         /* 0 = automatic (a function of m, n and the world size only), 1 = FP32 SIMT sweeps,
+                           2 = tensor-core sweeps (3xTF32 compact-WY products on tcgen05).  Engine 2 needs an
+                           operand workspace of 6 x the factored columns: if it does not fit, plan creation
+                           fails with B200QR_ENOMEM -- the library never switches engine behind the caller. */
+    int reserved[4];
 } b200qr_opts;
 
 typedef struct b200qr_plan_s *b200qr_plan_t;
@@ -73,18 +78,6 @@ int         b200qr_copy(void *dst, const void *src, size_t bytes);
 /* Measured FP32 FFMA throughput of the current device in GFLOP/s (register-resident FMA loop
  * on every SM, best of 3 after a warm-up): the roofline denominator of the SIMT kernels.   */
 int         b200qr_measure_fp32_peak(double *gflops, int iters);
-/* SM cycles per tile of the panel kernels run by one warp: cycles4 = {GEQRT alone, TSQRT alone,
- * GEQRT / TSQRT with eight FFMA-bound warps on the same SM}.  Diagnostic for the scheduler design. */
-int         b200qr_probe_panel(long long *cycles4, int reps);
-/* SM cycles per tile of `nwarps` (<= 16) independent one-warp TSQRT chains sharing one SM: cycles[w] for warp w.  Diagnostic
- * for the tall-skinny plan of DESIGN.md section 8 (how many chains an SM runs at the speed of one). */
-int b200qr_probe_panel_chains(long long *cycles, int reps, int nwarps);
-/* tcgen05 building-block check (see csrc/umma_probe.cu): hA 32 x 128 column-major, hV 32 x 32 column-major,
- * hW 128 x 32 row-major or NULL; hZ <- A^T V (128 x 32 row-major, 3xTF32 on the tensor cores);
- * hD2 <- A^T - W V^T when hW is given. */
-int         b200qr_probe_umma(const float *hA, const float *hV, const float *hW, float *hZ, float *hD2);
-int         b200qr_probe_umma_rate(long long *out8, int reps);   /* cycles of reps*4 tcgen05.mma (tf32, M=128, K=8): N=32,64,128,256 x {1,2} accumulators */
-int         b200qr_probe_umma_rate2(long long *out2, int reps);  /* one vs two issuing threads, reps*4 MMAs each (N = 32) */
 
 /* ---- plan: workspace + schedule for one (m, n) shape ----------------------------
  * Replaces the per-call cudaMalloc of task grid / queue / tau in cudaQRTask
@@ -94,7 +87,7 @@ int  b200qr_plan_create(b200qr_plan_t *plan, int m, int n, const b200qr_opts *op
 int  b200qr_plan_destroy(b200qr_plan_t plan);
 int  b200qr_plan_grid(b200qr_plan_t plan);               /* CTAs the kernel launches with */
 int  b200qr_plan_debug_counters(b200qr_plan_t plan, unsigned long long *out, int n);   /* opts.trace == 3: phase timers of the tensor-core engine */
-int  b200qr_plan_variant(b200qr_plan_t plan);            /* 1, 2: SIMT sweeps (1 / 2 columns per thread); 3, 4: tcgen05 sweeps */
+int  b200qr_plan_variant(b200qr_plan_t plan);            /* 1, 2: FP32 SIMT sweeps (1 / 2 matrix columns per thread); 5: tcgen05 sweeps */
 long b200qr_plan_tile_tasks(b200qr_plan_t plan);         /* sum_k (p-k)(q-k)  (gpucalc.cu:1546-1559) */
 long b200qr_plan_macro_tasks(b200qr_plan_t plan);        /* panel + column-sweep tasks actually queued */
 

@@ -58,6 +58,57 @@ def test_two_ranks_on_one_device_match_single_gpu(cuda, qr, po, m, n):
         rk.close()
 
 
+@pytest.mark.parametrize("m,n", [(2048, 2048), (4096, 3072)])
+def test_tensor_core_engine_two_ranks_on_one_device(cuda, qr, po, m, n):
+    """The multi-GPU form of the tensor-core engine (b200qr_opts.engine = 2: operand tiles TMA-stored into EVERY rank's
+    workspace by the panel owner, progress words pushed into every rank's array) with both ranks on one device in a
+    single cooperative launch -- the same code path a 2-GPU run takes, peer pointers included, runnable on a 1-GPU
+    box.  The result must equal the single-GPU engine's bit for bit and the oracle within the engine's tolerance."""
+    torch = cuda
+    a = po.randzo(m, n)
+    ranks = [qr.DistRank(m, n, r, 2, share_device=2, engine=2) for r in range(2)]
+    assert all(rk.variant == 5 for rk in ranks) and ranks[0].block == 4
+    qr.dist_connect_local(ranks)
+    for rk in ranks:
+        rk.upload(a.ctypes.data)
+    for rep in range(2):                               # twice: the second run starts from the first one's final words
+        for rk in ranks:
+            rk.upload(a.ctypes.data)
+        qr.dist_factor_group(ranks, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+    out, tau = gather(ranks, m, n)
+    d = torch.from_numpy(a).cuda()
+    dt = torch.zeros_like(d)
+    plan = qr.Plan(m, n, engine=2)
+    s = torch.cuda.current_stream().cuda_stream
+    plan.factor(d.data_ptr(), m, s)
+    plan.tau_to_reference(dt.data_ptr(), m, s)
+    torch.cuda.synchronize()
+    assert np.array_equal(out, d.cpu().numpy())
+    assert np.array_equal(tau, dt.cpu().numpy())
+    plan.close()
+    ref_out, _ = po.tiled_qr(a, m, n)
+    from qr_checks import r_rel_err_up_to_row_sign
+    err, flips = r_rel_err_up_to_row_sign(out, ref_out, m, n)
+    assert err <= 5e-4 and flips <= 16, (err, flips)
+    for rk in ranks:
+        rk.close()
+
+
+def test_ranks_must_agree_on_the_plan(cuda, qr):
+    """b200qr_dist_connect refuses peers whose plan differs (kernel variant, distribution block, shape): the exported
+    handle blob carries those facts (a rank that chose another engine would own other columns)."""
+    import ctypes as C
+    a = qr.DistRank(2048, 2048, 0, 2, share_device=2, engine=2)
+    b = qr.DistRank(2048, 2048, 1, 2, share_device=2, engine=1)
+    assert a.variant == 5 and b.variant == 2
+    blobs = [a.export(), b.export()]
+    for rk in (a, b):
+        rc = qr.lib().b200qr_dist_connect(rk._h, C.c_char_p(b"".join(blobs)))
+        assert rc == -1, rc                              # B200QR_EINVAL, in both directions
+    a.close(); b.close()
+
+
 def test_tensor_core_engine_on_two_real_gpus(cuda):
     """The multi-GPU form of the tensor-core engine (operand tiles broadcast by TMA stores into every rank's workspace)
     must give the single-GPU engine's result bit for bit.  Needs two visible GPUs (skipped on a one-GPU box)."""

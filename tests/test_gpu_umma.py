@@ -1,4 +1,4 @@
-"""tcgen05 building blocks (csrc/qr_umma.cuh, csrc/umma_probe.cu): TMA 128B-swizzled tiles ->
+"""tcgen05 building blocks (csrc/qr_umma.cuh, csrc/probes/umma_probe.cu): TMA 128B-swizzled tiles ->
 3xTF32 split -> tcgen05.mma kind::tf32 into TMEM -> tcgen05.ld, against float64 references.
 Stated tolerance: 3xTF32 keeps ~2^-21 per product; |err| <= 2e-6 * K * max|a| * max|b|."""
 import ctypes as C
@@ -17,7 +17,7 @@ def test_umma_products_match_float64(cuda, qr):
     Z = np.zeros((128, 32), dtype=np.float32)
     D2 = np.zeros((128, 32), dtype=np.float32)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    qr.check(qr.lib().b200qr_probe_umma(p(A), p(V), p(W), p(Z), p(D2)), "b200qr_probe_umma")
+    qr.check(qr.probe_lib().b200qr_probe_umma(p(A), p(V), p(W), p(Z), p(D2)), "b200qr_probe_umma")
     Am = A.T.astype(np.float64)                                  # (32 rows, 128 cols)
     Vm = V.T.astype(np.float64)                                  # (32 rows, 32 reflectors)
     Zref = Am.T @ Vm                                             # Z[m][n] = sum_r A[r][m] V[r][n]

@@ -3,7 +3,7 @@ import os, sys, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import gpu_tiled_qr_decomposition_b200 as q
-L = q.lib()
+L = q.probe_lib()
 L.b200qr_probe_umma_mode.argtypes = [C.c_void_p] * 5 + [C.c_int]
 rng = np.random.default_rng(7)
 A = rng.uniform(-1, 1, (128, 32)).astype(np.float32)

@@ -4,7 +4,7 @@ import numpy as np
 import gpu_tiled_qr_decomposition_b200 as q
 reps = 256
 out = np.zeros(8, dtype=np.int64)
-L = q.lib()
+L = q.probe_lib()
 L.b200qr_probe_umma_rate.argtypes = [C.c_void_p, C.c_int]
 for _ in range(2):
     q.check(L.b200qr_probe_umma_rate(out.ctypes.data_as(C.c_void_p), reps), "probe")

@@ -51,3 +51,14 @@ conc = [(int(((pan[:, 1] <= t) & (pan[:, 2] >= t)).sum())) for t in ts]
 print("active panels at 5%..95% of the run:", conc)
 print("far-sweep pace median over steps: %.2f us; near-sweep pace median: %.2f us; panel pace median %.2f us" % (
     np.median(far[:, 3]), np.median(near[:, 3]), np.median(pan[:p - 2, 3])))
+lag = np.diff(pan[:, 1])
+print("lag between consecutive panel starts (us): median %.1f, p10 %.1f, p90 %.1f; sum %.0f us of %.0f us total" % (
+    np.median(lag), np.percentile(lag, 10), np.percentile(lag, 90), lag.sum(), span))
+geq = []
+off = 0
+for k in range(p):
+    cnt = (p - k) * (p - k)
+    r = tr[off]                       # (k, k, k): GEQRT
+    geq.append((r[5] - r[4]) / 1e3)
+    off += cnt
+print("GEQRT duration median %.2f us" % np.median(geq))
