@@ -32,7 +32,11 @@ EXPORTS = (
     "b200qr_dist_connect_local", "b200qr_dist_factor_group",
     "b200qr_batched_workspace_floats", "b200qr_batched_factor", "b200qr_batched_last_cuda_error",
     "b200qr_tsqr_create", "b200qr_tsqr_create_streaming", "b200qr_tsqr_stream_block_rows", "b200qr_tsqr_create_rstack", "b200qr_tsqr_destroy", "b200qr_tsqr_levels", "b200qr_tsqr_factor",
-    "b200qr_apply_q", "b200qr_release_cache", "cudaQRTask", "cudaQRFull", "testDAPP", "doCUDADAPP",
+    "b200qr_apply_q", "b200qr_form_q", "b200qr_trsm_upper", "b200qr_solve_ls",
+    "b200qr_any_create", "b200qr_any_destroy", "b200qr_any_padded_rows", "b200qr_any_padded_cols", "b200qr_any_factor",
+    "b200qr_any_get_r", "b200qr_any_apply_q", "b200qr_any_solve_ls", "b200qr_any_factored", "b200qr_any_tau",
+    "b200qr_frontend_last_cuda_error",
+    "b200qr_release_cache", "cudaQRTask", "cudaQRFull", "testDAPP", "doCUDADAPP",
 )
 
 
@@ -169,6 +173,21 @@ def lib():
         L.b200qr_tsqr_factor.argtypes = [vp, vp, C.c_longlong, vp, vp]
         L.b200qr_release_cache.restype = None
         L.b200qr_apply_q.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp]
+        L.b200qr_form_q.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, vp]
+        L.b200qr_trsm_upper.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp]
+        L.b200qr_solve_ls.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, vp]
+        L.b200qr_any_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(Opts)]
+        L.b200qr_any_destroy.argtypes = [vp]
+        L.b200qr_any_padded_rows.argtypes = [vp]
+        L.b200qr_any_padded_cols.argtypes = [vp]
+        L.b200qr_any_factor.argtypes = [vp, vp, C.c_int, vp]
+        L.b200qr_any_get_r.argtypes = [vp, vp, C.c_int, vp]
+        L.b200qr_any_apply_q.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp]
+        L.b200qr_any_solve_ls.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp]
+        L.b200qr_any_factored.argtypes = [vp]
+        L.b200qr_any_factored.restype = vp
+        L.b200qr_any_tau.argtypes = [vp]
+        L.b200qr_any_tau.restype = vp
         L.cudaQRTask.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
         L.cudaQRTask.restype = None
         L.cudaQRFull.argtypes = [vp, C.c_int, C.c_int]
@@ -243,6 +262,42 @@ class Plan:
     def close(self):
         if self._h:
             lib().b200qr_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class AnyQR:
+    """Arbitrary-size front-end (b200qr_any_*): m, n need not be multiples of 32."""
+
+    def __init__(self, m, n, engine=0):
+        self.m, self.n = m, n
+        self._h = C.c_void_p()
+        o = Opts()
+        o.engine = int(engine)
+        check(lib().b200qr_any_create(C.byref(self._h), m, n, C.byref(o)), "b200qr_any_create")
+
+    def factor(self, dA_ptr, ldm, stream=0):
+        check(lib().b200qr_any_factor(self._h, C.c_void_p(dA_ptr), ldm, C.c_void_p(stream)), "b200qr_any_factor")
+
+    def get_r(self, dR_ptr, ldr, stream=0):
+        check(lib().b200qr_any_get_r(self._h, C.c_void_p(dR_ptr), ldr, C.c_void_p(stream)), "b200qr_any_get_r")
+
+    def apply_q(self, dC_ptr, ldc, ncols, transpose, stream=0):
+        check(lib().b200qr_any_apply_q(self._h, C.c_void_p(dC_ptr), ldc, ncols, int(transpose), C.c_void_p(stream)),
+              "b200qr_any_apply_q")
+
+    def solve_ls(self, dB_ptr, ldb, nrhs, dX_ptr, ldx, stream=0):
+        check(lib().b200qr_any_solve_ls(self._h, C.c_void_p(dB_ptr), ldb, nrhs, C.c_void_p(dX_ptr), ldx, C.c_void_p(stream)),
+              "b200qr_any_solve_ls")
+
+    def close(self):
+        if self._h:
+            lib().b200qr_any_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

@@ -271,6 +271,13 @@ __global__ void __launch_bounds__(256, MINB) tsqr_strip_kernel(const StripArgs a
     for (long long r0 = row0 + (TRI ? n : 0); r0 < row1; r0 += SRB, tau_out += n) {
         const int nr = (int)(row1 - r0 < SRB ? row1 - r0 : SRB);     // a multiple of 4
         const int c0 = TRI ? (int)((r0 - row0) % n) : 0;    // first column of this block that is not all zeros
+        // Start-up of a strip (the triangle is empty when it begins): after `seen` rows the stack [R; block] has rank
+        // <= seen + SRB, so only the reflectors c < c_end are determined by the data.  Behind them the block's columns
+        // are zero in exact arithmetic -- rounding noise here, whose sign would pick the sign of that row of R when
+        // the next block gives it mass -- so the block stops there: H = I (tau = 0, V = 0) for c >= c_end.  The oracle
+        // does the same (oracle_tsqrt_lead), which is what pins R and every reflector block at any width n.
+        const long long seen = r0 - row0;
+        const int c_end = (TRI || seen + SRB >= n) ? n : (int)(seen + SRB);
         float rc_next = 0.f;                                // R(c0, j): this thread's own store of an earlier block
         if (j >= c0) rc_next = __ldcg(Rg + c0 * n - (c0 * (c0 - 1)) / 2 + (j - c0));
         float b[SRB];
@@ -293,7 +300,7 @@ __global__ void __launch_bounds__(256, MINB) tsqr_strip_kernel(const StripArgs a
         float ssq = sumsq();
         if (TRI) __syncthreads();                           // the broadcast slots of the previous block (c0 may be odd or even)
 #pragma unroll 1
-        for (int c = c0; c < n; ++c) {
+        for (int c = c0; c < c_end; ++c) {
             float *x = xs + (c & 1) * SRB;
             float *h2 = hs + (c & 1) * 2;
             const int off = c * n - (c * (c - 1)) / 2;
@@ -344,6 +351,11 @@ __global__ void __launch_bounds__(256, MINB) tsqr_strip_kernel(const StripArgs a
                 }
             }
         }
+        if (!TRI && j >= c_end) {                           // start-up block: columns behind the last determined reflector
+            for (int r = 0; r < nr; r += 4) *reinterpret_cast<float4 *>(col + r0 + r) = make_float4(0.f, 0.f, 0.f, 0.f);
+            tau_out[j] = 0.f;
+        }
+        if (!TRI && c_end < n) __syncthreads();             // (the broadcast slots: the next block starts at c = 0 again)
     }
     float *rcol = a.Rout + (size_t)j * a.ldr + (size_t)blockIdx.x * n;
     for (int c = 0; c < n; ++c) rcol[c] = (c <= j) ? __ldcg(Rg + c * n - (c * (c - 1)) / 2 + (j - c)) : 0.f;

@@ -183,6 +183,33 @@ int b200qr_tsqr_factor(b200qr_tsqr_t t, float *dA, long long ldm, float *dR, voi
 int b200qr_apply_q(const float *dA, int m, int n, int ldm, const float *dTauCompact, float *dC, int ldc, int ncols,
                    int transpose, void *stream);
 
+/* Q(:, 0:ncols) of a factored matrix, explicitly: dQ (m x ncols, ldq) <- Q I(:, 0:ncols); ncols % 32 == 0, ncols <= m. */
+int b200qr_form_q(const float *dA, int m, int n, int ldm, const float *dTauCompact, float *dQ, int ldq, int ncols, void *stream);
+/* X <- R^-1 X for the n x n upper triangle R of a factored matrix (dR = its first element, ldr): dB is n x nrhs (ldb). */
+int b200qr_trsm_upper(const float *dR, int n, int ldr, float *dB, int ldb, int nrhs, void *stream);
+/* Least squares min |A x - b| with the factored A (m >= n, full column rank): dB (m x nrhs, ldb, nrhs % 32 == 0) is
+ * overwritten with Q^T B, whose first n rows are then overwritten with the solution X = R^-1 (Q^T B)(0:n, :). */
+int b200qr_solve_ls(const float *dA, int m, int n, int ldm, const float *dTauCompact, float *dB, int ldb, int nrhs, void *stream);
+
+/* ---- arbitrary sizes: the reference truncates m and n to multiples of 32 (qrdecomp.c:162,
+ * gpucalc.cu:1582); this front-end embeds the m x n matrix in a zero-padded (mp x np) device buffer owned by the handle
+ * (mp, np = m, n rounded up to 32), factors that, and serves R, Q and least-squares solves for the REAL sizes.  The m x n
+ * part of the factored buffer is the factorisation of A: padded rows carry zero reflector entries, padded columns the
+ * reference's zero-column case (qrdecomp.c:1219).  b200qr_any_factored / _tau expose the padded result (ld = mp) in the
+ * library's usual layout.  Every pointer is a device pointer; calls are asynchronous on `stream`. */
+typedef struct b200qr_any_s *b200qr_any_t;
+int  b200qr_any_create(b200qr_any_t *h, int m, int n, const b200qr_opts *opts);
+int  b200qr_any_destroy(b200qr_any_t h);
+int  b200qr_any_padded_rows(b200qr_any_t h);
+int  b200qr_any_padded_cols(b200qr_any_t h);
+int  b200qr_any_factor(b200qr_any_t h, const float *dA, int ldm, void *stream);          /* dA: m x n, not modified */
+int  b200qr_any_get_r(b200qr_any_t h, float *dR, int ldr, void *stream);                /* min(m,n) x n, upper */
+int  b200qr_any_apply_q(b200qr_any_t h, float *dC, int ldc, int ncols, int transpose, void *stream);   /* C: m x ncols */
+int  b200qr_any_solve_ls(b200qr_any_t h, const float *dB, int ldb, int nrhs, float *dX, int ldx, void *stream);
+const float *b200qr_any_factored(b200qr_any_t h);
+const float *b200qr_any_tau(b200qr_any_t h);
+int  b200qr_frontend_last_cuda_error(void);
+
 /* cudaQRTask keeps its plan and device buffer between calls of the same shape; this frees them. */
 void b200qr_release_cache(void);
 

@@ -29,6 +29,12 @@ def build(force=False):
         need = True
     if need:
         subprocess.run(["make", "-C", HERE, "all"], check=True, capture_output=True)
+    # the reference's own self-test binary, linked against the B200 library (needs /root/reference and libqrb200.so)
+    qlib = os.path.join(os.path.dirname(HERE), "gpu_tiled_qr_decomposition_b200", "libqrb200.so")
+    exe = os.path.join(HERE, "_ref", "ref_selftest")
+    if os.path.isfile("/root/reference/qrdecomp.c") and os.path.exists(qlib) and (
+            force or not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(qlib)):
+        subprocess.run(["make", "-C", HERE, "selftest"], check=True, capture_output=True)
 
 
 def _bind(lib):
@@ -36,6 +42,7 @@ def _bind(lib):
     lib.oracle_fill_randzo.argtypes = [_f32p, C.c_int, C.c_int, C.c_int]
     lib.oracle_geqrt.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_int, _f32p]
     lib.oracle_tsqrt.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]
+    lib.oracle_tsqrt_lead.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]
     lib.oracle_unmqr.argtypes = [_f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
     lib.oracle_tsmqr.argtypes = [_f32p, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int]
     for name in ("oracle_tiled_qr_sched", "oracle_tiled_qr_static"):
@@ -112,7 +119,9 @@ def tsqr_stream(a, m, n, block_rows):
     """Tall-skinny QR by ONE TSQRT chain whose tile is as wide as the matrix -- the recurrence the streaming engine of
     the product runs per strip: R starts as the empty n x n triangle and every block of `block_rows` rows is one call of
     the TSQRT restatement (oracle_tsqrt = qrdecomp.c:689-721 STSQRF + 1243-1272 calcvkDouble + 647-687 updateDoubleQ_WY,
-    whose tile sizes are parameters) with ma = n, mb = block_rows.  `a`: (n, m) float32 storage of the column-major m x n
+    whose tile sizes are parameters) with ma = n, mb = block_rows.  While fewer than n rows have gone by, a block only
+    determines the reflectors k < rows seen so far (oracle_tsqrt_lead: the columns behind them are zero up to rounding,
+    and both implementations set them to zero rather than let the sign of that noise pick the sign of a row of R).  `a`: (n, m) float32 storage of the column-major m x n
     matrix.  Returns (V, tau, R): V (n, m) storage with every block replaced by its reflector block V2, tau
     (m / block_rows, n), R (n, n) storage, upper triangular ([column, row])."""
     assert m % block_rows == 0
@@ -128,7 +137,8 @@ def tsqr_stream(a, m, n, block_rows):
         buf[:, n:] = V[:, rows]
         t = np.zeros(n, dtype=np.float32)
         top = buf.reshape(-1)
-        L.oracle_tsqrt(top, top[n:], t, n, block_rows, n, ld, work)
+        nref = min(n, (bi + 1) * block_rows)
+        L.oracle_tsqrt_lead(top, top[n:], t, n, block_rows, nref, n, ld, work)
         V[:, rows] = buf[:, n:]
         tau[bi] = t
     return V, tau, np.ascontiguousarray(buf[:, :n])

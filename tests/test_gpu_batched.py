@@ -172,15 +172,15 @@ def test_tsqr_rstack_reduction(cuda, qr, count, n):
     assert (torch.max(torch.abs(Rm - sg[:, None] * R64)) / torch.max(torch.abs(R64))).item() <= 1e-4
 
 
-@pytest.mark.parametrize("m,n", [(1536, 64)])
+@pytest.mark.parametrize("m,n", [(1536, 64), (768, 256), (1536, 256), (1488, 224)])
 def test_tsqr_streaming_matches_oracle_elementwise(cuda, qr, po, m, n):
     """One strip of the streaming engine against the oracle's chain of n-wide TSQRT steps (pyoracle.tsqr_stream = the
-    reference's STSQRF restated, qrdecomp.c:689-721) on the same input and block height: R and every reflector block
-    agree element by element (float32 rounding only: FMA, split sums, tau = 1 + |x0| / nrm vs 2 / (1 + |v|^2)).
-    Only shapes whose rank-deficient start-up phase is short are comparable this way: at n = 256 (six 48-row blocks
-    before the triangle has full rank) the pivots of the undetermined columns are rounding noise whose signs decide the
-    final row signs, and even two float32 CPU implementations part ways (profiles/r1_measurements.md); there the
-    criterion is R up to row signs (test_tsqr_streaming_r_factor)."""
+    reference's STSQRF restated, qrdecomp.c:689-721) on the same input and block height: R, its diagonal signs and EVERY
+    reflector block agree element by element (float32 rounding only: FMA, split sums, tau = 1 + |x0| / nrm vs
+    2 / (1 + |v|^2)), at BASELINE.json's width n = 256 too.  Round 1 could not pin n = 256: a strip starts from an empty
+    triangle, and while fewer than n rows have gone by the trailing columns of a block are rounding noise whose signs
+    decided the final row signs.  Both implementations now stop a start-up block at the last column its rows determine
+    (oracle_tsqrt_lead; tsqr_strip_kernel's c_end), which is what those columns are mathematically: zero."""
     torch = cuda
     rng = np.random.default_rng(5 * m + n)
     a = rng.uniform(-1, 1, (n, m)).astype(np.float32)
@@ -198,9 +198,37 @@ def test_tsqr_streaming_matches_oracle_elementwise(cuda, qr, po, m, n):
     scale = float(np.max(np.abs(R_ref)))
     assert np.max(np.abs(R.cpu().numpy() - R_ref)) <= 1e-4 * scale
     assert np.all(np.sign(np.diag(R.cpu().numpy())) == np.sign(np.diag(R_ref)))      # same sign convention
-    # Reflector blocks: only where they are determined by the data.  The chain starts from an EMPTY triangle, so until n
-    # rows have gone by the stacked matrix [R; block] is rank deficient and the trailing reflectors of those first blocks
-    # are directions of rounding noise (x ~ 1e-7, v = x / |x|): valid, but different in any two implementations.
-    first = -(-n // rb) * rb
-    assert first < m
-    assert np.max(np.abs(d.cpu().numpy()[:, first:] - V_ref[:, first:])) <= 1e-4
+    assert np.max(np.abs(d.cpu().numpy() - V_ref)) <= 1e-4       # every reflector block, start-up blocks included
+    if n > rb:                                                   # the undetermined columns of the first block are exactly zero
+        assert not d.cpu().numpy()[rb:, :rb].any()
+
+
+def test_tsqr_full_size(cuda, qr):
+    """BASELINE.json configs[3] at full size, 4 194 304 x 256 on one GPU: R^T R = A^T A to 50 eps, R upper triangular,
+    and R equal up to row signs to the Cholesky factor of the float64 Gram matrix (= the R of a QR of A, unique up to row
+    signs; cond(A) ~ 1 for this input, so the float64 Cholesky is exact to ~1e-13) within 1e-4 max|R|."""
+    torch = cuda
+    m, n = 4194304, 256
+    free, _ = torch.cuda.mem_get_info()
+    if free < 3 * 4 * m * n:
+        pytest.skip("needs 12 GB of free device memory")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.rand((n, m), generator=g, device="cuda", dtype=torch.float32) * 2 - 1
+    d = A.clone()
+    t = qr.Tsqr(m, n)
+    R = torch.zeros((n, n), device="cuda")
+    t.factor(d.data_ptr(), m, R.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    t.close()
+    del d
+    G = torch.zeros((n, n), dtype=torch.float64, device="cuda")
+    for c in range(0, m, 1 << 20):
+        blk = A[:, c:c + (1 << 20)].double()
+        G += blk @ blk.t()
+    Rm = R.t().double()
+    assert torch.count_nonzero(torch.tril(Rm, -1)) == 0
+    assert (torch.linalg.norm(Rm.t() @ Rm - G) / torch.linalg.norm(G)).item() <= 50 * float(np.finfo(np.float32).eps)
+    Rc = torch.linalg.cholesky(G).t()                            # upper, positive diagonal
+    s = torch.sign(torch.diagonal(Rm))
+    assert (s != 0).all()
+    assert (torch.max(torch.abs(Rm - s[:, None] * Rc)) / torch.max(torch.abs(Rc))).item() <= 1e-4

@@ -241,3 +241,22 @@ def test_full_size_properties(cuda, qr, po):
     s = torch.sign(torch.diagonal(R64)) * torch.sign(torch.diagonal(R))
     err = (torch.max(torch.abs(R - s[:, None] * R64)) / torch.max(torch.abs(R64))).item()
     assert err <= RTOL_R, err
+
+
+@pytest.mark.parametrize("tiles", [4, 16, 32])
+def test_reference_selftest_against_the_b200_library(cuda, po, tiles):
+    """the reference's OWN driver -- main -> tiledQR (qrdecomp.c:27-130), unmodified,
+    compiled from /root/reference by oracle/Makefile `selftest` and linked against libqrb200.so -- factors its srand(5)
+    RANDZO matrix on its CPU path (taskQRP_threads), calls cudaQRTask (ours), and compares every element with its own
+    checkEqual (1e-3 absolute, qrdecomp.c:1322-1352).  It must print "Correct." (qrdecomp.c:103-113).  `tiles` = 32 is
+    BASELINE.json configs[0]: 1024 x 1024 at the reference's tile size."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "ref_selftest")
+    assert os.path.exists(exe), "oracle/_ref/ref_selftest is missing: run __graft_entry__.build() where /root/reference exists"
+    r = subprocess.run([exe, str(tiles)], capture_output=True, text=True, timeout=300, env=dict(os.environ, QRB200_QUIET="0"))
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    assert "Correct." in r.stdout and "Failure." not in r.stdout, r.stdout[-1000:]
+    n = tiles * 32
+    tasks = sum((tiles - k) * (tiles - k) for k in range(tiles))
+    assert "(%d,%d)" % (n, n) in r.stdout and "%d tasks" % tasks in r.stdout     # the legacy prints (gpucalc.cu:1557)
