@@ -464,17 +464,21 @@ def tsqr_multi(torch, dist, q, rank, world, steps, fp32_tf, peaks, peak_src, m=4
     """BASELINE.json configs[3] with the rows split over the ranks: local reduction, all-gather of the W R factors
     (the path's one exchange step), redundant top reduction on every rank."""
     m_local = m // world
+    stream = torch.cuda.current_stream().cuda_stream
     g = torch.Generator(device="cuda").manual_seed(100 + rank)
     A0 = torch.rand((n, m_local), generator=g, device="cuda") * 2 - 1
     d = torch.empty_like(A0)
     R = torch.zeros((n, n), device="cuda")
-    td = q.TsqrDist(m_local, n, world)
+    td = q.TsqrDistC(m_local, n, rank, world)                 # the C ABI: exchange over peer memory inside the stream
+    blobs = [None] * world
+    dist.all_gather_object(blobs, td.export())
+    td.connect(blobs)
     ms_tot = 0.0
     for it in range(steps + 2):
         d.copy_(A0)
         torch.cuda.synchronize(); dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); td.factor(d, R); e1.record()
+        e0.record(); td.factor(d.data_ptr(), m_local, R.data_ptr(), stream); e1.record()
         torch.cuda.synchronize(); dist.barrier()
         if it >= 2:
             ms_tot += e0.elapsed_time(e1)
@@ -494,8 +498,9 @@ def tsqr_multi(torch, dist, q, rank, world, steps, fp32_tf, peaks, peak_src, m=4
     err = (torch.linalg.norm(Rm.t() @ Rm - G) / torch.linalg.norm(G)).item()
     td.close()
     flops = qr_flops(m, n)
-    return {"workload": "TSQR %dx%d, rows split over %d GPUs (%d rows each), all-gather of the R factors + redundant top "
-                        "reduction" % (m, n, world, m_local), "ms": ms, "value": flops / ms * 1e-6, "unit": "GFLOP/s",
+    return {"workload": "TSQR %dx%d, rows split over %d GPUs (%d rows each; local engine: %s), R factors exchanged over peer "
+                        "memory inside the stream (b200qr_tsqr_dist_*: no collective library on the data path) + redundant top "
+                        "reduction" % (m, n, world, m_local, td.mode), "ms": ms, "value": flops / ms * 1e-6, "unit": "GFLOP/s",
             "same_R_on_all_ranks": bool(same), "gram_rel_err": err, "exchange_bytes_per_rank": 4 * n * n * (world - 1),
             "roofline": roofline_hbm("tsqr local reduction + top reduction", "%dx%d" % (m, n), 8.0 * m * n, flops, ms, fp32_tf,
                                      peaks, peak_src, world)}

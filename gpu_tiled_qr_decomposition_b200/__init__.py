@@ -31,7 +31,10 @@ EXPORTS = (
     "b200qr_dist_owner", "b200qr_dist_grid", "b200qr_dist_variant", "b200qr_dist_read_trace", "b200qr_dist_tile_tasks", "b200qr_dist_reset", "b200qr_dist_factor",
     "b200qr_dist_connect_local", "b200qr_dist_factor_group",
     "b200qr_batched_workspace_floats", "b200qr_batched_factor", "b200qr_batched_last_cuda_error",
-    "b200qr_tsqr_create", "b200qr_tsqr_create_streaming", "b200qr_tsqr_stream_block_rows", "b200qr_tsqr_create_rstack", "b200qr_tsqr_destroy", "b200qr_tsqr_levels", "b200qr_tsqr_factor",
+    "b200qr_tsqr_create", "b200qr_tsqr_create_streaming", "b200qr_tsqr_create_tiles", "b200qr_tsqr_leaves", "b200qr_tsqr_stream_block_rows", "b200qr_tsqr_create_rstack", "b200qr_tsqr_destroy", "b200qr_tsqr_levels", "b200qr_tsqr_factor",
+    "b200qr_tsqr_dist_create", "b200qr_tsqr_dist_destroy", "b200qr_tsqr_dist_handle_bytes", "b200qr_tsqr_dist_export",
+    "b200qr_tsqr_dist_connect", "b200qr_tsqr_dist_connect_local", "b200qr_tsqr_dist_factor", "b200qr_tsqr_dist_factor_begin",
+    "b200qr_tsqr_dist_factor_end", "b200qr_tsqr_dist_local_r",
     "b200qr_apply_q", "b200qr_form_q", "b200qr_trsm_upper", "b200qr_solve_ls",
     "b200qr_any_create", "b200qr_any_destroy", "b200qr_any_padded_rows", "b200qr_any_padded_cols", "b200qr_any_factor",
     "b200qr_any_get_r", "b200qr_any_apply_q", "b200qr_any_solve_ls", "b200qr_any_factored", "b200qr_any_tau",
@@ -166,11 +169,23 @@ def lib():
         L.b200qr_batched_factor.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int, vp, vp, vp]
         L.b200qr_tsqr_create.argtypes = [C.POINTER(vp), C.c_longlong, C.c_int, C.c_int, C.c_int]
         L.b200qr_tsqr_create_streaming.argtypes = [C.POINTER(vp), C.c_longlong, C.c_int, C.c_int]
+        L.b200qr_tsqr_create_tiles.argtypes = [C.POINTER(vp), C.c_longlong, C.c_int, C.c_int]
+        L.b200qr_tsqr_leaves.argtypes = [vp]
         L.b200qr_tsqr_stream_block_rows.argtypes = [vp]
         L.b200qr_tsqr_create_rstack.argtypes = [C.POINTER(vp), C.c_int, C.c_int]
         L.b200qr_tsqr_destroy.argtypes = [vp]
         L.b200qr_tsqr_levels.argtypes = [vp]
         L.b200qr_tsqr_factor.argtypes = [vp, vp, C.c_longlong, vp, vp]
+        L.b200qr_tsqr_dist_create.argtypes = [C.POINTER(vp), C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.b200qr_tsqr_dist_destroy.argtypes = [vp]
+        L.b200qr_tsqr_dist_export.argtypes = [vp, vp]
+        L.b200qr_tsqr_dist_connect.argtypes = [vp, vp]
+        L.b200qr_tsqr_dist_connect_local.argtypes = [C.POINTER(vp), C.c_int]
+        L.b200qr_tsqr_dist_factor.argtypes = [vp, vp, C.c_longlong, vp, vp]
+        L.b200qr_tsqr_dist_factor_begin.argtypes = [vp, vp, C.c_longlong, vp]
+        L.b200qr_tsqr_dist_factor_end.argtypes = [vp, vp, vp]
+        L.b200qr_tsqr_dist_local_r.argtypes = [vp]
+        L.b200qr_tsqr_dist_local_r.restype = vp
         L.b200qr_release_cache.restype = None
         L.b200qr_apply_q.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp]
         L.b200qr_form_q.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, vp]
@@ -418,15 +433,24 @@ class DistRank:
             self._h = C.c_void_p()
 
 
+DEFAULT_TSQR_MODE = "stream"
+
+
 class Tsqr:
     """Tall-skinny QR of an m x n matrix, n <= 256 (b200qr_tsqr_*).  Default: the streaming engine (strips of rows, the
     n x n triangle resident in shared memory); leaf_rows > 0 selects the leaf-batch tree (reference tile layout per leaf)."""
 
-    def __init__(self, m, n, strips=0, leaf_rows=0, fanin=4, rstack=0):
+    def __init__(self, m, n, strips=0, leaf_rows=0, fanin=4, rstack=0, mode=None):
+        """mode: "stream" (streaming engine), "tiles" (one warp per leaf on the batched tile kernel); None = the
+        library default (QRB200_TSQR_MODE overrides)."""
         self.m, self.n = m, n
         self._h = C.c_void_p()
+        mode = mode or os.environ.get("QRB200_TSQR_MODE") or DEFAULT_TSQR_MODE
+        self.mode = "rstack" if rstack else ("leaf-batch tree" if leaf_rows else mode)
         if rstack:                  # m = rstack * n rows: a stack of `rstack` upper-triangular factors
             check(lib().b200qr_tsqr_create_rstack(C.byref(self._h), rstack, n), "b200qr_tsqr_create_rstack")
+        elif not leaf_rows and mode == "tiles":
+            check(lib().b200qr_tsqr_create_tiles(C.byref(self._h), m, n, strips), "b200qr_tsqr_create_tiles")
         elif leaf_rows:
             check(lib().b200qr_tsqr_create(C.byref(self._h), m, n, leaf_rows, fanin), "b200qr_tsqr_create")
         else:
@@ -435,6 +459,16 @@ class Tsqr:
     @property
     def levels(self):
         return lib().b200qr_tsqr_levels(self._h)
+
+    @property
+    def kernel_name(self):
+        return "batched_warp_kernel" if self.mode == "tiles" else "tsqr_strip_kernel"
+
+    def describe(self):
+        if self.mode == "tiles":
+            return "tile engine: %d leaves of %d rows, one warp each; %d pairwise levels" % (
+                lib().b200qr_tsqr_leaves(self._h), self.m // max(1, lib().b200qr_tsqr_leaves(self._h)), self.levels - 1)
+        return "%s engine, %d levels" % (self.mode, self.levels)
 
     def factor(self, dA_ptr, ldm, dR_ptr, stream=0):
         """dA (m x n, column-major, ldm) is overwritten with the leaf reflectors, dR (n x n, ld = n) receives R."""
@@ -508,6 +542,47 @@ class TsqrDist:
         for t in (self._local, self._top):
             if t is not None:
                 t.close()
+
+
+class TsqrDistC:
+    """One rank of the multi-GPU TSQR behind the C ABI (b200qr_tsqr_dist_*): the R factors are exchanged over peer
+    memory from inside the stream, no collective library on the data path.  export() / connect(blobs) like DistRank."""
+
+    def __init__(self, m_local, n, rank, world, mode=None):
+        self.m_local, self.n, self.rank, self.world = m_local, n, rank, world
+        mode = mode or os.environ.get("QRB200_TSQR_MODE") or DEFAULT_TSQR_MODE
+        self.mode = mode
+        self._h = C.c_void_p()
+        check(lib().b200qr_tsqr_dist_create(C.byref(self._h), m_local, n, rank, world, 1 if mode == "tiles" else 0),
+              "b200qr_tsqr_dist_create")
+
+    def export(self):
+        buf = C.create_string_buffer(lib().b200qr_tsqr_dist_handle_bytes())
+        check(lib().b200qr_tsqr_dist_export(self._h, buf), "b200qr_tsqr_dist_export")
+        return buf.raw
+
+    def connect(self, blobs):
+        check(lib().b200qr_tsqr_dist_connect(self._h, C.c_char_p(b"".join(blobs))), "b200qr_tsqr_dist_connect")
+
+    def factor(self, dA_ptr, ldm, dR_ptr, stream=0):
+        check(lib().b200qr_tsqr_dist_factor(self._h, C.c_void_p(dA_ptr), ldm, C.c_void_p(dR_ptr), C.c_void_p(stream)),
+              "b200qr_tsqr_dist_factor")
+
+    def factor_begin(self, dA_ptr, ldm, stream=0):
+        check(lib().b200qr_tsqr_dist_factor_begin(self._h, C.c_void_p(dA_ptr), ldm, C.c_void_p(stream)), "b200qr_tsqr_dist_factor_begin")
+
+    def factor_end(self, dR_ptr, stream=0):
+        check(lib().b200qr_tsqr_dist_factor_end(self._h, C.c_void_p(dR_ptr), C.c_void_p(stream)), "b200qr_tsqr_dist_factor_end")
+
+    def close(self):
+        if self._h:
+            lib().b200qr_tsqr_dist_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+def tsqr_dist_connect_local(ranks):
+    arr = (C.c_void_p * len(ranks))(*[r._h for r in ranks])
+    check(lib().b200qr_tsqr_dist_connect_local(arr, len(ranks)), "b200qr_tsqr_dist_connect_local")
 
 
 def dist_connect_local(ranks):

@@ -21,6 +21,7 @@
 #include "../../include/qrb200.h"
 
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 namespace qrb200 {
@@ -114,6 +115,111 @@ __global__ void __launch_bounds__(BQ * 32, 2) batched_tiledqr_kernel(const Batch
 #pragma unroll
             for (int r = 0; r < TB; ++r) x[r] = top[r * TB + lane];
             store_col_gmem(tile(k, w), x);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Round 2: ONE WARP PER PROBLEM, phases in lock-step across the CTA.
+// What round 1's kernel above measured (21.2 ms for 10 000 x 256^2; profiles/r1_measurements.md): its warps alternate
+// between FFMA-bound update chains and latency-bound panel chains at different times, and this SM's schedulers let an
+// FFMA-bound warp starve a panel chain that shares its sub-partition (tools/probe_panel.py: a TSQRT takes 162k cycles
+// instead of 13k next to eight FFMA warps) -- while the panel chain is the critical path of every problem.
+// Here a CTA of BW warps works on BW problems at a time, one per warp, and all warps are in the SAME phase of their
+// problem: step k's panel (GEQRT + TSQRT chain; sixteen latency-bound chains share the SM, 46 tiles per 100k cycles --
+// the best panel throughput an SM has), a CTA barrier, step k's update of the trailing tile columns, two columns per
+// pass (every warp FFMA-bound at once), a barrier.  No warp ever waits for another one's data: the panel tiles, their
+// tau and the trailing tiles of a problem are written and read back by the same threads.  Same four tile kernels, same
+// operation order per tile and same output layout as cudaQRTask on each problem (bit-identical: bench.py checks it).
+constexpr int BW_FLOATS = 1088 + 1024 + 1024 + 32 + 64;         // Rs / V tile, top row of column 0 (V2 out while a panel), top row of column 1, tau, slots
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <int BW>                                               // warps = problems in flight per CTA
+__global__ void __launch_bounds__(BW * 32, 1) batched_warp_kernel(const BatchArgs a)
+{
+    extern __shared__ __align__(16) float bsm[];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *Vs = bsm + w * BW_FLOATS;
+    float *top0 = Vs + 1088, *top1 = top0 + 1024, *ts = top1 + 1024, *xs = ts + 32;
+    const int p = a.p, q = a.q, K = p < q ? p : q, ldm = a.ldm;
+    // the problems are dealt to the CTAs evenly up front (no tail of one late CTA); a CTA takes its share BW at a time
+    const int per = a.nprob / (int)gridDim.x, rem = a.nprob % (int)gridDim.x;
+    const int first = (int)blockIdx.x * per + ((int)blockIdx.x < rem ? (int)blockIdx.x : rem);
+    const int count = per + ((int)blockIdx.x < rem ? 1 : 0);
+
+    for (int b0 = 0; b0 < count; b0 += BW) {
+        const bool live = b0 + w < count;
+        const int b = first + b0 + w;
+        float *M = a.A + (size_t)(live ? b : first) * a.strideA;
+        float *tb = a.tauc + (size_t)(live ? b : first) * K * p * TB;
+        auto tile = [&](int I, int J) { return M + (size_t)(J * TB + lane) * ldm + I * TB; };
+        for (int k = 0; k < K; ++k) {
+            if (live) {
+                // ---- panel of step k: GEQRT + TSQRT chain (qrdecomp.c:532-557, 689-721)
+                float x[TB];
+                load_col_gmem(x, tile(k, k));
+                if (k + 1 < p) prefetch_l2(tile(k + 1, k));
+                float t = geqrt_warp(x, xs, lane);
+                store_col_gmem(tile(k, k), x);
+                tb[((size_t)k * p + k) * TB + lane] = t;
+#pragma unroll
+                for (int r = 0; r < TB; ++r) Vs[r * 33 + lane] = x[r];
+                __syncwarp();
+                for (int i = k + 1; i < p; ++i) {
+                    load_col_gmem(x, tile(i, k));
+                    if (i + 1 < p) prefetch_l2(tile(i + 1, k));
+                    float ti = tsqrt_warp(x, Vs, xs, top0, lane);
+                    store_col_gmem(tile(i, k), x);
+                    tb[((size_t)k * p + i) * TB + lane] = ti;
+                }
+                float *rcol = tile(k, k);
+#pragma unroll
+                for (int r = 0; r < TB; ++r)
+                    if (r <= lane) rcol[r] = Vs[r * 33 + lane];
+            }
+            __syncthreads();
+            if (live) {
+                // ---- step k applied to the trailing tile columns, two at a time (qrdecomp.c:620-644, 736-762)
+                for (int j = k + 1; j < q; j += 2) {
+                    const bool two = j + 1 < q;
+                    float x0[TB], x1[TB];
+                    auto stage_v = [&](int i) {              // reflector tile (i, k) and its tau -> shared memory
+                        load_col_gmem(x0, tile(i, k));       // (this thread wrote this very column in the panel phase)
+                        store_col_smem(Vs + lane * TB, x0);
+                        ts[lane] = tb[((size_t)k * p + i) * TB + lane];
+                        __syncwarp();
+                    };
+                    stage_v(k);
+                    load_col_gmem(x0, tile(k, j));
+                    if (two) load_col_gmem(x1, tile(k, j + 1));
+                    if (two) apply_reflectors_nc<2, false>(x0, x1, nullptr, nullptr, 0, Vs, ts);
+                    else apply_reflectors_nc<1, false>(x0, x0, nullptr, nullptr, 0, Vs, ts);
+#pragma unroll
+                    for (int r = 0; r < TB; ++r) { top0[r * TB + lane] = x0[r]; if (two) top1[r * TB + lane] = x1[r]; }
+                    for (int i = k + 1; i < p; ++i) {
+                        __syncwarp();                        // everyone is done with the previous reflector tile
+                        stage_v(i);
+                        load_col_gmem(x0, tile(i, j));
+                        if (two) load_col_gmem(x1, tile(i, j + 1));
+                        if (i + 1 < p) { prefetch_l2(tile(i + 1, k)); prefetch_l2(tile(i + 1, j)); if (two) prefetch_l2(tile(i + 1, j + 1)); }
+                        if (two) apply_reflectors_nc<2, true>(x0, x1, top0 + lane, top1 + lane, TB, Vs, ts);
+                        else apply_reflectors_nc<1, true>(x0, x0, top0 + lane, top0 + lane, TB, Vs, ts);
+                        store_col_gmem(tile(i, j), x0);
+                        if (two) store_col_gmem(tile(i, j + 1), x1);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int r = 0; r < TB; ++r) x0[r] = top0[r * TB + lane];
+                    store_col_gmem(tile(k, j), x0);
+                    if (two) {
+#pragma unroll
+                        for (int r = 0; r < TB; ++r) x1[r] = top1[r * TB + lane];
+                        store_col_gmem(tile(k, j + 1), x1);
+                    }
+                }
+            }
+            __syncthreads();
         }
     }
 }
@@ -366,6 +472,37 @@ __global__ void __launch_bounds__(256, MINB) tsqr_strip_kernel(const StripArgs a
 // two-barrier form in which the next owner broadcasts its column before its scalar work (56.9 ms against 48.0 ms at
 // 4 194 304 x 256) and a form with eight reflectors per barrier and a compact-WY sweep by the other warps (58.9 ms).
 
+// ---- exchange step of the multi-GPU TSQR over peer memory (b200qr_tsqr_dist_*): flags are epoch numbers, monotonic
+__global__ void tsqr_signal_kernel(int *const *peer_flags, int world, int rank, int epoch)
+{
+    const int r = threadIdx.x;
+    if (r < world) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(peer_flags[r] + rank), "r"(epoch) : "memory");
+    }
+}
+__global__ void tsqr_wait_kernel(const int *flags, int world, int epoch, unsigned long long limit_ns)
+{
+    const int r = threadIdx.x;
+    if (r < world) {
+        unsigned long long t0 = 0;
+        unsigned spins = 0;
+        for (;;) {
+            int v;
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
+            if (v >= epoch) break;
+            __nanosleep(200);
+            if (((++spins) & 0xfffu) == 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > limit_ns) __trap();        // a peer never arrived: fail loudly instead of hanging the GPU
+            }
+        }
+    }
+    __syncthreads();
+}
+
 }  // namespace qrb200
 
 using namespace qrb200;
@@ -380,24 +517,39 @@ static thread_local int g_batched_cuda = 0;
 static int batched_launch(float *dA, int m, int n, int ldm, long long strideA, int nprob, float *dTau, int *dCounter,
                           cudaStream_t stream)
 {
-    // the shared-memory opt-in is a per-device attribute and the grid cap a per-device number: both are taken for the
-    // CURRENT device on every call (two cheap runtime calls), so a process may use several GPUs and threads
-    const int smem = BQ * WARP_FLOATS * (int)sizeof(float);
-    int grid_cap = 0;
-    {
-        int dev = 0, sms = 0, occ = 0;
-        CKB(cudaGetDevice(&dev));
-        CKB(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        CKB(cudaFuncSetAttribute(batched_tiledqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, batched_tiledqr_kernel, BQ * 32, smem));
-        grid_cap = sms * (occ > 0 ? occ : 1);
-    }
+    // the shared-memory opt-in is a per-device attribute and the grid a per-device number: both are taken for the
+    // CURRENT device on every call (cheap runtime calls), so a process may use several GPUs and threads
+    int dev = 0, sms = 0;
+    CKB(cudaGetDevice(&dev));
+    CKB(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     BatchArgs a;
     a.A = dA; a.strideA = strideA; a.ldm = ldm; a.p = m / TB; a.q = n / TB; a.nprob = nprob;
     a.tauc = dTau; a.counter = dCounter;
-    CKB(cudaMemsetAsync(dCounter, 0, sizeof(int), stream));
-    const int grid = nprob < grid_cap ? nprob : grid_cap;
-    batched_tiledqr_kernel<<<grid, BQ * 32, smem, stream>>>(a);
+    const char *force = getenv("QRB200_BATCHED");           // "colwarp" / "warp": A/B runs
+    const bool few = nprob < 4 * sms;                        // too few problems to give every warp of the device one
+    if ((few && !(force && force[0] == 'w')) || (force && force[0] == 'c')) {
+        // one CTA per problem, warp w = tile column w: more parallelism inside a problem (the tree levels of the TSQR)
+        const int smem = BQ * WARP_FLOATS * (int)sizeof(float);
+        int occ = 0;
+        CKB(cudaFuncSetAttribute(batched_tiledqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CKB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, batched_tiledqr_kernel, BQ * 32, smem));
+        const int grid_cap = sms * (occ > 0 ? occ : 1);
+        CKB(cudaMemsetAsync(dCounter, 0, sizeof(int), stream));
+        batched_tiledqr_kernel<<<nprob < grid_cap ? nprob : grid_cap, BQ * 32, smem, stream>>>(a);
+    } else {
+        // sixteen warps: 128 registers per thread (a few spills in the update phase), twelve: 168 and none
+        int bw = 16;
+        if (const char *e = getenv("QRB200_BATCHED_WARPS")) { const int v = atoi(e); if (v == 12 || v == 16) bw = v; }
+        const int smem = bw * BW_FLOATS * (int)sizeof(float);
+        const int grid = nprob < sms ? nprob : sms;
+        if (bw == 16) {
+            CKB(cudaFuncSetAttribute(batched_warp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            batched_warp_kernel<16><<<grid, 16 * 32, smem, stream>>>(a);
+        } else {
+            CKB(cudaFuncSetAttribute(batched_warp_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            batched_warp_kernel<12><<<grid, 12 * 32, smem, stream>>>(a);
+        }
+    }
     CKB(cudaGetLastError());
     return B200QR_OK;
 }
@@ -419,6 +571,7 @@ struct b200qr_tsqr_s {
     std::vector<SLevel> slevels;
     bool rstack = false;                // b200qr_tsqr_create_rstack: the input IS level 0's stack of factors
     bool streaming = false;
+    bool leaf_tiles = false;            // b200qr_tsqr_create_tiles: leaves by the batched tile kernel, pairwise levels above
 };
 
 extern "C" {
@@ -569,6 +722,36 @@ int b200qr_tsqr_create_streaming(b200qr_tsqr_t *out, long long m, int n, int str
     return B200QR_OK;
 }
 
+// Tile engine for the leaves: the rows are cut into `leaves` equal leaves (<= 0: as many as the device has warps for,
+// sixteen per SM, among the divisors of m that leave whole tile rows), every leaf is one problem of the batched tile
+// kernel -- one warp per leaf, a flat tree of 32 x 32 TSQRT tiles down each of its n / 32 tile columns, exactly the
+// reference's chain (gridscheduler.c:136-154) per leaf -- and the leaves' R factors are reduced pairwise by the
+// streaming engine's triangular levels.  Reflectors: leaves in dA in the reference's tile layout, tau in the plan.
+int b200qr_tsqr_create_tiles(b200qr_tsqr_t *out, long long m, int n, int leaves)
+{
+    if (!out || n <= 0 || n % TB || n > BQ * TB || m <= 0 || m % TB || m < n) return B200QR_EINVAL;
+    if (leaves <= 0) {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            return B200QR_ECUDA;
+        for (leaves = sms * 16; leaves > 1; --leaves)
+            if (m % leaves == 0 && (m / leaves) % TB == 0 && m / leaves >= n) break;
+    }
+    if (leaves < 1 || m % leaves || (m / leaves) % TB || m / leaves < n || m / leaves > 0x7fffffffLL) return B200QR_EINVAL;
+    b200qr_tsqr_s *t = new b200qr_tsqr_s;
+    t->m = m; t->n = n; t->leaf_rows = (int)(m / leaves); t->fanin = 2; t->streaming = true; t->leaf_tiles = true;
+    t->strips = leaves;
+    auto fail = [&]() { b200qr_tsqr_destroy(t); return B200QR_ENOMEM; };
+    if (cudaMalloc(&t->d_counter, sizeof(int)) != cudaSuccess) return fail();
+    if (cudaMalloc(&t->d_leaf_tau, sizeof(float) * (size_t)m * (n / TB)) != cudaSuccess) return fail();     // per leaf: q * leaf_rows
+    if (cudaMalloc(&t->d_rws, sizeof(float) * (size_t)((leaves + 1) / 2) * (n * (n + 1) / 2)) != cudaSuccess) return fail();
+    if (build_slevels(t, leaves, false) != B200QR_OK) return fail();
+    *out = t;
+    return B200QR_OK;
+}
+
+int b200qr_tsqr_leaves(b200qr_tsqr_t t) { return t ? t->strips : B200QR_EINVAL; }
+
 int b200qr_tsqr_destroy(b200qr_tsqr_t t)
 {
     if (!t) return B200QR_EINVAL;
@@ -599,7 +782,12 @@ int b200qr_tsqr_factor(b200qr_tsqr_t t, float *dA, long long ldm, float *dR, voi
     if (t->streaming) {
         StripArgs a;
         a.n = n; a.Rws = t->d_rws;
-        if (!t->rstack) {
+        if (t->leaf_tiles) {
+            rc = batched_launch(dA, t->leaf_rows, n, (int)ldm, t->leaf_rows, t->strips, t->d_leaf_tau, t->d_counter, stream);
+            if (rc != B200QR_OK) return rc;
+            gather_r_kernel<<<1024, 256, 0, stream>>>(dA, t->leaf_rows, (int)ldm, n, t->strips, t->strips > 1 ? t->slevels[0].stack : dR);
+            CKB(cudaGetLastError());
+        } else if (!t->rstack) {
             CKB(cudaMemsetAsync(t->d_rws, 0, sizeof(float) * (size_t)t->strips * (n * (n + 1) / 2), stream));
             a.A = dA; a.ldm = ldm; a.rows = t->m; a.rows_per_strip = t->rows_per_strip; a.blocks_per_strip = t->blocks_per_strip;
             a.tau = t->d_stream_tau;
@@ -654,5 +842,161 @@ int b200qr_tsqr_factor(b200qr_tsqr_t t, float *dA, long long ldm, float *dR, voi
     CKB(cudaGetLastError());
     return B200QR_OK;
 }
+
+}  // extern "C"
+
+
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU TSQR behind the C ABI (BASELINE.json configs[3] at 2 / 4 / 8 GPUs): rank r owns a contiguous block
+// of m_local rows.  factor(): (1) the rank reduces its block to an n x n factor with the single-GPU engine; (2) the
+// exchange -- the path's one real communication step, W x n x n floats -- happens over peer memory: the rank copies its
+// factor into slot `rank` of EVERY rank's stack buffer (cudaMemcpy2DAsync over NVLink, on the caller's stream), raises
+// its epoch flag in every rank's flag array (system-scope release) and waits until all W flags of its own array show
+// the epoch (system-scope acquire); (3) every rank reduces the stack of W factors redundantly (b200qr_tsqr_create_rstack),
+// so all ranks end with the same R.  No host synchronisation, no collective library: the caller only moves the handle
+// blobs once (export -> all-gather by any means -> connect).  Two stack buffers alternate by epoch, so a rank that is
+// already in its next factorisation cannot overwrite a stack a slower peer is still reducing (it cannot get two epochs
+// ahead: its wait needs the peer's next flag).
+struct tsqr_dist_blob { cudaIpcMemHandle_t mem; int n, world, rank; long long m_local; };
+
+struct b200qr_tsqr_dist_s {
+    long long m_local;
+    int n, rank, world, epoch = 0;
+    b200qr_tsqr_t local = nullptr, top = nullptr;
+    unsigned char *d_mem = nullptr;            // [2 stacks of world*n*n floats][flags: world ints (padded to 256 B)]
+    unsigned char *peer_mem[8] = {};
+    void *opened[8] = {};
+    float *d_rlocal = nullptr;
+    int **d_peer_flags = nullptr;              // device array of world pointers
+    int connected = 0;
+    size_t stack_bytes() const { return sizeof(float) * (size_t)world * n * n; }
+    float *stack(unsigned char *base, int which) const { return reinterpret_cast<float *>(base + which * stack_bytes()); }
+    int *flags(unsigned char *base) const { return reinterpret_cast<int *>(base + 2 * stack_bytes()); }
+};
+
+extern "C" {
+
+int b200qr_tsqr_dist_create(b200qr_tsqr_dist_t *out, long long m_local, int n, int rank, int world, int tiles)
+{
+    if (!out || world < 1 || world > 8 || rank < 0 || rank >= world || n <= 0 || n % TB || n > BQ * TB || m_local < n || m_local % TB)
+        return B200QR_EINVAL;
+    b200qr_tsqr_dist_s *h = new b200qr_tsqr_dist_s;
+    h->m_local = m_local; h->n = n; h->rank = rank; h->world = world;
+    int rc = tiles ? b200qr_tsqr_create_tiles(&h->local, m_local, n, 0) : b200qr_tsqr_create_streaming(&h->local, m_local, n, 0);
+    if (rc == B200QR_OK && world > 1) rc = b200qr_tsqr_create_rstack(&h->top, world, n);
+    const size_t bytes = 2 * h->stack_bytes() + 256;
+    if (rc == B200QR_OK && cudaMalloc(&h->d_mem, bytes) != cudaSuccess) rc = B200QR_ENOMEM;
+    if (rc == B200QR_OK && cudaMalloc(&h->d_rlocal, sizeof(float) * (size_t)n * n) != cudaSuccess) rc = B200QR_ENOMEM;
+    if (rc == B200QR_OK && cudaMalloc(&h->d_peer_flags, sizeof(int *) * 8) != cudaSuccess) rc = B200QR_ENOMEM;
+    if (rc == B200QR_OK && cudaMemset(h->d_mem, 0, bytes) != cudaSuccess) rc = B200QR_ECUDA;
+    if (rc != B200QR_OK) { b200qr_tsqr_dist_destroy(h); return rc; }
+    h->peer_mem[rank] = h->d_mem;
+    if (world == 1) h->connected = 1;
+    *out = h;
+    return B200QR_OK;
+}
+
+int b200qr_tsqr_dist_destroy(b200qr_tsqr_dist_t h)
+{
+    if (!h) return B200QR_EINVAL;
+    for (void *p : h->opened) if (p) cudaIpcCloseMemHandle(p);
+    if (h->local) b200qr_tsqr_destroy(h->local);
+    if (h->top) b200qr_tsqr_destroy(h->top);
+    cudaFree(h->d_mem); cudaFree(h->d_rlocal); cudaFree(h->d_peer_flags);
+    delete h;
+    return B200QR_OK;
+}
+
+int b200qr_tsqr_dist_handle_bytes(void) { return (int)sizeof(tsqr_dist_blob); }
+
+int b200qr_tsqr_dist_export(b200qr_tsqr_dist_t h, void *out_bytes)
+{
+    if (!h || !out_bytes) return B200QR_EINVAL;
+    tsqr_dist_blob b;
+    memset(&b, 0, sizeof b);
+    CKB(cudaIpcGetMemHandle(&b.mem, h->d_mem));
+    b.n = h->n; b.world = h->world; b.rank = h->rank; b.m_local = h->m_local;
+    memcpy(out_bytes, &b, sizeof b);
+    return B200QR_OK;
+}
+
+static int tsqr_dist_finish_connect(b200qr_tsqr_dist_s *h)
+{
+    int *fl[8] = {};
+    for (int r = 0; r < h->world; ++r) fl[r] = h->flags(h->peer_mem[r]);
+    CKB(cudaMemcpy(h->d_peer_flags, fl, sizeof fl, cudaMemcpyHostToDevice));
+    h->connected = 1;
+    return B200QR_OK;
+}
+
+int b200qr_tsqr_dist_connect(b200qr_tsqr_dist_t h, const void *all_bytes)
+{
+    if (!h || !all_bytes) return B200QR_EINVAL;
+    const tsqr_dist_blob *blobs = (const tsqr_dist_blob *)all_bytes;
+    for (int r = 0; r < h->world; ++r)
+        if (blobs[r].n != h->n || blobs[r].world != h->world || blobs[r].rank != r) return B200QR_EINVAL;
+    for (int r = 0; r < h->world; ++r) {
+        if (r == h->rank) continue;
+        void *p = nullptr;
+        CKB(cudaIpcOpenMemHandle(&p, blobs[r].mem, cudaIpcMemLazyEnablePeerAccess));
+        h->opened[r] = p;
+        h->peer_mem[r] = (unsigned char *)p;
+    }
+    return tsqr_dist_finish_connect(h);
+}
+
+// rank objects that live in ONE process (tests; several GPUs driven by one process): plain pointers instead of IPC handles
+int b200qr_tsqr_dist_connect_local(b200qr_tsqr_dist_t *all, int world)
+{
+    if (!all || world < 1 || world > 8) return B200QR_EINVAL;
+    for (int r = 0; r < world; ++r) {
+        if (!all[r] || all[r]->world != world || all[r]->rank != r || all[r]->n != all[0]->n) return B200QR_EINVAL;
+        for (int o = 0; o < world; ++o) all[r]->peer_mem[o] = all[o]->d_mem;
+        int rc = tsqr_dist_finish_connect(all[r]);
+        if (rc != B200QR_OK) return rc;
+    }
+    return B200QR_OK;
+}
+
+// split form (a single process driving several rank objects must run phase 1 of every rank before any phase 2):
+// phase 1 = local reduction + exchange + signal, phase 2 = wait + top reduction.  b200qr_tsqr_dist_factor = both.
+int b200qr_tsqr_dist_factor_begin(b200qr_tsqr_dist_t h, float *dA, long long ldm, void *stream_)
+{
+    if (!h || !h->connected || !dA) return B200QR_EINVAL;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int n = h->n, W = h->world;
+    int rc = b200qr_tsqr_factor(h->local, dA, ldm, h->d_rlocal, stream);
+    if (rc != B200QR_OK || W == 1) return rc;
+    const int e = ++h->epoch;
+    for (int r = 0; r < W; ++r)
+        CKB(cudaMemcpy2DAsync(h->stack(h->peer_mem[r], e & 1) + (size_t)h->rank * n, sizeof(float) * (size_t)W * n, h->d_rlocal,
+                              sizeof(float) * n, sizeof(float) * n, n, cudaMemcpyDeviceToDevice, stream));
+    tsqr_signal_kernel<<<1, 32, 0, stream>>>(h->d_peer_flags, W, h->rank, e);
+    CKB(cudaGetLastError());
+    return B200QR_OK;
+}
+
+int b200qr_tsqr_dist_factor_end(b200qr_tsqr_dist_t h, float *dR, void *stream_)
+{
+    if (!h || !h->connected || !dR) return B200QR_EINVAL;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int n = h->n, W = h->world;
+    if (W == 1) {
+        CKB(cudaMemcpyAsync(dR, h->d_rlocal, sizeof(float) * (size_t)n * n, cudaMemcpyDeviceToDevice, stream));
+        return B200QR_OK;
+    }
+    const char *wd = getenv("QRB200_WATCHDOG_MS");
+    tsqr_wait_kernel<<<1, 32, 0, stream>>>(h->flags(h->d_mem), W, h->epoch, (unsigned long long)(wd ? atol(wd) : 60000) * 1000000ull);
+    CKB(cudaGetLastError());
+    return b200qr_tsqr_factor(h->top, h->stack(h->d_mem, h->epoch & 1), (long long)W * n, dR, stream);
+}
+
+int b200qr_tsqr_dist_factor(b200qr_tsqr_dist_t h, float *dA, long long ldm, float *dR, void *stream)
+{
+    int rc = b200qr_tsqr_dist_factor_begin(h, dA, ldm, stream);
+    return rc != B200QR_OK ? rc : b200qr_tsqr_dist_factor_end(h, dR, stream);
+}
+
+const float *b200qr_tsqr_dist_local_r(b200qr_tsqr_dist_t h) { return h ? h->d_rlocal : nullptr; }
 
 }  // extern "C"

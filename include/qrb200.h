@@ -167,6 +167,12 @@ int b200qr_tsqr_create(b200qr_tsqr_t *t, long long m, int n, int leaf_rows, int 
  * and the strips' R factors are reduced by the leaf-batch tree, four at a time.  Reflectors stay in dA (one block of
  * rows x n per TSQRT step, strips of ceil(m / strips) rows rounded up to whole blocks) and in the plan (tree). */
 int b200qr_tsqr_create_streaming(b200qr_tsqr_t *t, long long m, int n, int strips);
+/* Tile engine for the same job: `leaves` equal leaves (<= 0: sixteen per SM, rounded down to a divisor of m), each factored
+ * by ONE WARP of the batched tile kernel as a flat tree of 32 x 32 TSQRT tiles per tile column (the reference's own chain,
+ * gridscheduler.c:136-154, per leaf; leaf reflectors in dA in the reference's tile layout), the leaves' R factors reduced
+ * pairwise by the streaming engine's triangular levels. */
+int b200qr_tsqr_create_tiles(b200qr_tsqr_t *t, long long m, int n, int leaves);
+int b200qr_tsqr_leaves(b200qr_tsqr_t t);             /* leaves (tile engine) or strips (streaming engine) */
 int b200qr_tsqr_stream_block_rows(b200qr_tsqr_t t);
 /* Reduction of `count` stacked n x n upper-triangular factors ((count*n) x n, column-major) to one by the streaming
  * engine's pairwise levels: the top of the multi-GPU TSQR (all-gather of the ranks' R factors, then every
@@ -175,6 +181,26 @@ int b200qr_tsqr_create_rstack(b200qr_tsqr_t *t, int count, int n);
 int b200qr_tsqr_destroy(b200qr_tsqr_t t);
 int b200qr_tsqr_levels(b200qr_tsqr_t t);
 int b200qr_tsqr_factor(b200qr_tsqr_t t, float *dA, long long ldm, float *dR, void *stream);
+
+/* ---- TSQR over several GPUs behind the C ABI (BASELINE.json configs[3] at 2 / 4 / 8 GPUs) -------------------------
+ * One rank (process) per GPU; rank r owns rows [r * m_local, (r + 1) * m_local).  factor(): local reduction -> the R
+ * factors are exchanged over peer memory (each rank copies its n x n factor into every rank's stack buffer over NVLink
+ * and raises an epoch flag there; nobody calls a collective library or synchronises on the host) -> every rank reduces
+ * the stack of W factors, so all ranks hold the same R.  Protocol: create -> export -> [all-gather the handle bytes]
+ * -> connect -> factor (any number of times, asynchronous on `stream`).  tiles != 0 selects the tile engine for the
+ * local reduction, 0 the streaming engine.  The reflectors stay in dA (local), in the plans (trees).            */
+typedef struct b200qr_tsqr_dist_s *b200qr_tsqr_dist_t;
+int b200qr_tsqr_dist_create(b200qr_tsqr_dist_t *h, long long m_local, int n, int rank, int world, int tiles);
+int b200qr_tsqr_dist_destroy(b200qr_tsqr_dist_t h);
+int b200qr_tsqr_dist_handle_bytes(void);
+int b200qr_tsqr_dist_export(b200qr_tsqr_dist_t h, void *out_bytes);
+int b200qr_tsqr_dist_connect(b200qr_tsqr_dist_t h, const void *all_bytes);            /* world blobs, rank order */
+int b200qr_tsqr_dist_connect_local(b200qr_tsqr_dist_t *all, int world);               /* rank objects of one process */
+int b200qr_tsqr_dist_factor(b200qr_tsqr_dist_t h, float *dA, long long ldm, float *dR, void *stream);
+/* the two halves of factor(), for a single process that drives several rank objects (all begins before any end) */
+int b200qr_tsqr_dist_factor_begin(b200qr_tsqr_dist_t h, float *dA, long long ldm, void *stream);
+int b200qr_tsqr_dist_factor_end(b200qr_tsqr_dist_t h, float *dR, void *stream);
+const float *b200qr_tsqr_dist_local_r(b200qr_tsqr_dist_t h);                          /* the rank's own n x n factor */
 
 /* ---- apply Q (the reference has no such routine, qrdecomp.c:1292 multAB is unused) ---
  * C <- Q^T C (transpose != 0) or Q C for the Q held implicitly by a factored matrix: dA = factored

@@ -59,6 +59,72 @@ def test_batched_equals_single_matrix_path(cuda, qr, po):
     plan.close()
 
 
+@pytest.mark.parametrize("warps", ["16", "12"])
+@pytest.mark.parametrize("m,n,nprob", [(256, 256, 1000), (512, 96, 700), (64, 160, 1203)])
+def test_batched_one_warp_per_problem_kernel(cuda, qr, po, monkeypatch, warps, m, n, nprob):
+    """Enough problems (>= 4 per SM) select the round-2 kernel -- one warp per problem, panel and update phases in
+    lock-step across the CTA (batched_warp_kernel, 16 or 12 warps per CTA).  Every problem must be bit-identical to
+    b200qr_factor_device on that matrix (same tile kernels, same operation order), which the oracle tests pin; a sample
+    is also compared with the oracle directly.  Odd tile-column counts exercise the single-column tail of the update."""
+    torch = cuda
+    monkeypatch.setenv("QRB200_BATCHED_WARPS", warps)
+    monkeypatch.setenv("QRB200_BATCHED", "warp")
+    rng = np.random.default_rng(m + n + nprob)
+    mats = rng.uniform(-1, 1, (nprob, n, m)).astype(np.float32)
+    mats[3, 5:9, :] = 0.0                                              # a problem with zero columns (degenerate reflectors)
+    out, tau = batched(qr, torch, mats, m, n)
+    per = tau.size // nprob
+    plan = qr.Plan(m, n)
+    s = torch.cuda.current_stream().cuda_stream
+    dt = torch.zeros((n, m), device="cuda")
+    for b in (0, 3, 15, 16, 17, nprob // 2, nprob - 2, nprob - 1):
+        d = torch.from_numpy(mats[b]).cuda()
+        plan.factor(d.data_ptr(), m, s)
+        plan.tau_to_reference(dt.data_ptr(), m, s)
+        torch.cuda.synchronize()
+        assert np.array_equal(out[b], d.cpu().numpy()), b
+        assert np.array_equal(expand_tau(tau[b * per:(b + 1) * per], m, n), dt.cpu().numpy()), b
+    plan.close()
+    for b in (1, nprob - 1):
+        ref_out, ref_tau = po.tiled_qr(mats[b], m, n)
+        assert np.max(np.abs(out[b] - ref_out)) <= 1e-4 * max(1.0, float(np.max(np.abs(ref_out))))
+    # every problem: R^T R = A^T A
+    R = np.triu(np.transpose(out, (0, 2, 1))[:, :min(m, n), :].astype(np.float64))
+    A = np.transpose(mats, (0, 2, 1)).astype(np.float64)
+    G = np.einsum("bij,bik->bjk", A, A)
+    RtR = np.einsum("bij,bik->bjk", R, R)
+    err = np.linalg.norm((RtR - G).reshape(nprob, -1), axis=1) / np.maximum(np.linalg.norm(G.reshape(nprob, -1), axis=1), 1e-30)
+    assert float(err.max()) <= 50 * float(np.finfo(np.float32).eps), float(err.max())
+
+
+@pytest.mark.parametrize("m,n,leaves", [(1 << 20, 256, 0), (65536, 128, 37 * 0 + 64), (40960, 256, 5), (8192, 32, 256)])
+def test_tsqr_tile_engine_r_factor(cuda, qr, m, n, leaves):
+    """TSQR with the leaves on the batched tile kernel (b200qr_tsqr_create_tiles: one warp per leaf, the reference's
+    flat TSQRT chain per leaf) and pairwise triangular levels above: R upper triangular, R^T R = A^T A, R equal to
+    float64 LAPACK's up to row signs within 1e-4 max|R|."""
+    torch = cuda
+    g = torch.Generator(device="cuda").manual_seed(17)
+    A = torch.rand((n, m), generator=g, device="cuda", dtype=torch.float32) * 2 - 1
+    d = A.clone()
+    t = qr.Tsqr(m, n, strips=leaves, mode="tiles")
+    R = torch.full((n, n), 7.0, dtype=torch.float32, device="cuda")
+    for _ in range(2):
+        d.copy_(A)
+        t.factor(d.data_ptr(), m, R.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert "tile engine" in t.describe()
+    t.close()
+    Rm = R.t().double()
+    assert torch.count_nonzero(torch.tril(Rm, -1)) == 0
+    Ad = A.t().double()
+    G = Ad.t() @ Ad
+    assert (torch.linalg.norm(Rm.t() @ Rm - G) / torch.linalg.norm(G)).item() <= 50 * float(np.finfo(np.float32).eps)
+    Rc = torch.linalg.cholesky(G).t()
+    sg = torch.sign(torch.diagonal(Rm))
+    assert (torch.max(torch.abs(Rm - sg[:, None] * Rc)) / torch.max(torch.abs(Rc))).item() <= 1e-4
+    assert torch.isfinite(d).all()
+
+
 @pytest.mark.parametrize("m,n,leaf,fanin", [(4096, 256, 512, 2), (8192, 128, 256, 4), (12288, 256, 2048, 4), (2048, 64, 2048, 2),
                                               (5120, 256, 512, 4)])
 def test_tsqr_r_factor(cuda, qr, m, n, leaf, fanin):
@@ -172,7 +238,7 @@ def test_tsqr_rstack_reduction(cuda, qr, count, n):
     assert (torch.max(torch.abs(Rm - sg[:, None] * R64)) / torch.max(torch.abs(R64))).item() <= 1e-4
 
 
-@pytest.mark.parametrize("m,n", [(1536, 64), (768, 256), (1536, 256), (1488, 224)])
+@pytest.mark.parametrize("m,n", [(1536, 64), (768, 256), (1536, 256), (1440, 224)])
 def test_tsqr_streaming_matches_oracle_elementwise(cuda, qr, po, m, n):
     """One strip of the streaming engine against the oracle's chain of n-wide TSQRT steps (pyoracle.tsqr_stream = the
     reference's STSQRF restated, qrdecomp.c:689-721) on the same input and block height: R, its diagonal signs and EVERY

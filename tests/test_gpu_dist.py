@@ -149,6 +149,35 @@ def test_tsqr_split_over_two_real_gpus(cuda):
     assert line["same_R_on_all_ranks"] and line["gram_rel_err"] <= 50 * float(np.finfo(np.float32).eps), line
 
 
+@pytest.mark.parametrize("world,mode", [(2, "stream"), (4, "tiles"), (3, "stream")])
+def test_tsqr_dist_c_abi_ranks_on_one_device(cuda, qr, world, mode):
+    """b200qr_tsqr_dist_* (the multi-GPU TSQR behind the C ABI: R factors exchanged over peer memory, epoch flags with
+    system-scope release / acquire, two alternating stack buffers) with all rank objects on one device and one stream:
+    every rank ends with the same R, R^T R = sum_r A_r^T A_r, also on the second and third call (epochs, buffer parity)."""
+    torch = cuda
+    m_local, n = 16384, 128
+    s = torch.cuda.current_stream().cuda_stream
+    ranks = [qr.TsqrDistC(m_local, n, r, world, mode=mode) for r in range(world)]
+    qr.tsqr_dist_connect_local(ranks)
+    g = torch.Generator(device="cuda").manual_seed(41)
+    for rep in range(3):
+        A = [torch.rand((n, m_local), generator=g, device="cuda") * 2 - 1 for _ in range(world)]
+        d = [a.clone() for a in A]
+        R = [torch.full((n, n), 3.0, device="cuda") for _ in range(world)]
+        for r in range(world):
+            ranks[r].factor_begin(d[r].data_ptr(), m_local, s)
+        for r in range(world):
+            ranks[r].factor_end(R[r].data_ptr(), s)
+        torch.cuda.synchronize()
+        assert all(torch.equal(R[0], x) for x in R)
+        Rm = R[0].t().double()
+        assert torch.count_nonzero(torch.tril(Rm, -1)) == 0
+        G = sum(a.double() @ a.double().t() for a in A)
+        assert (torch.linalg.norm(Rm.t() @ Rm - G) / torch.linalg.norm(G)).item() <= 50 * float(np.finfo(np.float32).eps)
+    for rk in ranks:
+        rk.close()
+
+
 def test_tsqr_dist_single_rank(cuda, qr):
     """TsqrDist with one rank = the plain streaming plan."""
     torch = cuda
