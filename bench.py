@@ -292,7 +292,7 @@ def extra_sweep(torch, q, L, fp32_tf, peaks, peak_src, steps, n=8192):
                 plan = q.TilePlan(n, n, b)
                 fn = lambda: plan.factor(d.data_ptr(), n, stream)
                 ms = timed(torch, fn, lambda: d.copy_(A0), max(1, min(steps, 3)), 1)
-                back, orth = plan.probe_accuracy(torch, d, A0)
+                back, orth = probe_accuracy(torch, plan, d, A0, n, n, 128)
                 row.update({"backward_err_n_eps": back, "orthogonality_n_eps": orth})
                 tf = flops / ms * 1e-9
                 row["roofline"] = {"bound": "fp32-simt", "achieved": tf, "peak": fp32_tf, "unit": "TFLOP/s", "frac": tf / fp32_tf,

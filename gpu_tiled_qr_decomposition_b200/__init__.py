@@ -39,6 +39,8 @@ EXPORTS = (
     "b200qr_any_create", "b200qr_any_destroy", "b200qr_any_padded_rows", "b200qr_any_padded_cols", "b200qr_any_factor",
     "b200qr_any_get_r", "b200qr_any_apply_q", "b200qr_any_solve_ls", "b200qr_any_factored", "b200qr_any_tau",
     "b200qr_frontend_last_cuda_error",
+    "b200qr_tiles_create", "b200qr_tiles_destroy", "b200qr_tiles_tile", "b200qr_tiles_factor", "b200qr_tiles_tau",
+    "b200qr_tiles_apply_q", "b200qr_tiles_last_cuda_error",
     "b200qr_release_cache", "cudaQRTask", "cudaQRFull", "testDAPP", "doCUDADAPP",
 )
 
@@ -203,6 +205,13 @@ def lib():
         L.b200qr_any_factored.restype = vp
         L.b200qr_any_tau.argtypes = [vp]
         L.b200qr_any_tau.restype = vp
+        L.b200qr_tiles_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int]
+        L.b200qr_tiles_destroy.argtypes = [vp]
+        L.b200qr_tiles_tile.argtypes = [vp]
+        L.b200qr_tiles_factor.argtypes = [vp, vp, C.c_int, vp]
+        L.b200qr_tiles_tau.argtypes = [vp]
+        L.b200qr_tiles_tau.restype = vp
+        L.b200qr_tiles_apply_q.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]
         L.cudaQRTask.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
         L.cudaQRTask.restype = None
         L.cudaQRFull.argtypes = [vp, C.c_int, C.c_int]
@@ -277,6 +286,51 @@ class Plan:
     def close(self):
         if self._h:
             lib().b200qr_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class TilePlan:
+    """Tiled QR at tile size b in {32, 64, 128} (b200qr_tiles_*: the non-default mode of BASELINE.json's tile-size
+    sweep; generic host-ordered kernels, own reflector layout = the reference's with 32 -> b)."""
+
+    def __init__(self, m, n, b):
+        self.m, self.n, self.b = m, n, b
+        self._h = C.c_void_p()
+        check(lib().b200qr_tiles_create(C.byref(self._h), m, n, b), "b200qr_tiles_create")
+
+    def factor(self, dptr, ldm, stream=0):
+        check(lib().b200qr_tiles_factor(self._h, C.c_void_p(dptr), ldm, C.c_void_p(stream)), "b200qr_tiles_factor")
+
+    @property
+    def tau_ptr(self):
+        return lib().b200qr_tiles_tau(self._h)
+
+    def apply_q(self, dA_ptr, ldm, dC_ptr, ldc, ncols, transpose, stream=0):
+        check(lib().b200qr_tiles_apply_q(self._h, C.c_void_p(dA_ptr), ldm, C.c_void_p(dC_ptr), ldc, ncols, int(transpose),
+                                         C.c_void_p(stream)), "b200qr_tiles_apply_q")
+
+    def tau_reference_layout(self):
+        """tau as the reference's tau matrix with 32 -> b (tile (i, k): rows 0..b-1 of the tile's first column)."""
+        import numpy as np
+        p, q, b = self.m // self.b, self.n // self.b, self.b
+        K = min(p, q)
+        tc = np.zeros((K, p, b), dtype=np.float32)
+        check(lib().b200qr_copy(tc.ctypes.data_as(C.c_void_p), C.c_void_p(self.tau_ptr), tc.nbytes), "b200qr_copy")
+        out = np.zeros((self.n, self.m), dtype=np.float32)
+        for k in range(K):
+            for i in range(k, p):
+                out[k * b, i * b:(i + 1) * b] = tc[k, i]
+        return out
+
+    def close(self):
+        if self._h:
+            lib().b200qr_tiles_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

@@ -537,8 +537,9 @@ static int batched_launch(float *dA, int m, int n, int ldm, long long strideA, i
         CKB(cudaMemsetAsync(dCounter, 0, sizeof(int), stream));
         batched_tiledqr_kernel<<<nprob < grid_cap ? nprob : grid_cap, BQ * 32, smem, stream>>>(a);
     } else {
-        // sixteen warps: 128 registers per thread (a few spills in the update phase), twelve: 168 and none
-        int bw = 16;
+        // twelve warps: 168 registers per thread, no spills -- 12.8 ms for 10 000 x 256^2 on B200; sixteen: 128 registers,
+        // 136 bytes of spills in the update phase -- 17.2 ms (round 1's kernel above: 18.1 ms with the round-2 panel kernels)
+        int bw = 12;
         if (const char *e = getenv("QRB200_BATCHED_WARPS")) { const int v = atoi(e); if (v == 12 || v == 16) bw = v; }
         const int smem = bw * BW_FLOATS * (int)sizeof(float);
         const int grid = nprob < sms ? nprob : sms;

@@ -236,6 +236,22 @@ const float *b200qr_any_factored(b200qr_any_t h);
 const float *b200qr_any_tau(b200qr_any_t h);
 int  b200qr_frontend_last_cuda_error(void);
 
+/* ---- other tile sizes (BASELINE.json configs[1]: tile-size sweep 32 / 64 / 128) -------------------------------------
+ * The reference bakes 32 into both paths (gpucalc.cu:1582, qrdecomp.c:506) and the drop-in layout is defined on 32 x 32
+ * tiles; this is the documented non-default mode for b = 64 and 128 (32 is accepted too: the same generic kernels,
+ * the host-ordered baseline the persistent engines are compared with).  Same four tile kernels with the tile size a
+ * parameter, the reference's flat-tree order, host-ordered launches (csrc/qr_tiles.cu).  Output layout = the
+ * reference's with 32 -> b; tau compact [(k*p + i)*b + r], p = m / b.  m % b == 0, n % b == 0.  Asynchronous on `stream`. */
+typedef struct b200qr_tileplan_s *b200qr_tileplan_t;
+int  b200qr_tiles_create(b200qr_tileplan_t *plan, int m, int n, int b);
+int  b200qr_tiles_destroy(b200qr_tileplan_t plan);
+int  b200qr_tiles_tile(b200qr_tileplan_t plan);
+int  b200qr_tiles_factor(b200qr_tileplan_t plan, float *dA, int ldm, void *stream);
+const float *b200qr_tiles_tau(b200qr_tileplan_t plan);
+/* C (m x ncols, ncols % b == 0) <- Q^T C (transpose != 0) or Q C with the reflectors of a matrix factored by this plan */
+int  b200qr_tiles_apply_q(b200qr_tileplan_t plan, const float *dA, int ldm, float *dC, int ldc, int ncols, int transpose, void *stream);
+int  b200qr_tiles_last_cuda_error(void);
+
 /* cudaQRTask keeps its plan and device buffer between calls of the same shape; this frees them. */
 void b200qr_release_cache(void);
 

@@ -1,0 +1,53 @@
+"""Tile sizes 32 / 64 / 128 (BASELINE.json configs[1]'s sweep; csrc/qr_tiles.cu) against the oracle run at the same tile
+size (oracle/tiledqr_oracle.c takes b as a parameter: the reference's kernels with the literal 32 of qrdecomp.c:506
+replaced by b, as SURVEY 8c prescribes).  Same tolerances as the b = 32 parity tests: elementwise 1e-4 max|R|, tau
+1e-5 * n / 32 absolute, backward error and orthogonality <= 5 n eps."""
+import numpy as np
+import pytest
+
+from qr_checks import probe_accuracy
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("b", [32, 64, 128])
+@pytest.mark.parametrize("m,n", [(512, 512), (768, 512), (256, 384), (1024, 128)])
+def test_tile_sizes_match_oracle(cuda, qr, po, b, m, n):
+    torch = cuda
+    if m % b or n % b:
+        pytest.skip("shape is not a multiple of the tile size")
+    a = po.randzo(m, n)
+    d = torch.from_numpy(a).cuda()
+    plan = qr.TilePlan(m, n, b)
+    plan.factor(d.data_ptr(), m, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    out = d.cpu().numpy()
+    tau = plan.tau_reference_layout()
+    ref_out, ref_tau = po.tiled_qr(a, m, n, b=b)
+    scale = max(1.0, float(np.max(np.abs(ref_out))))
+    assert np.max(np.abs(out - ref_out)) <= 1e-4 * scale
+    assert np.max(np.abs(tau - ref_tau)) <= 1e-5 * max(1, n // 32)
+    assert np.all(np.sign(np.diag(out.T[:min(m, n), :min(m, n)])) == np.sign(np.diag(ref_out.T[:min(m, n), :min(m, n)])))
+    back, orth, _ = po.quality(a, out, tau, m, n, b=b)
+    assert back <= 5 and orth <= 5, (back, orth)
+    plan.close()
+
+
+@pytest.mark.parametrize("b", [32, 64, 128])
+def test_tile_sizes_r_is_tile_size_independent_up_to_sign(cuda, qr, b):
+    """R does not depend on the tile size except for row signs; accuracy through the plan's own apply-Q at 2048^2."""
+    torch = cuda
+    n = 2048
+    g = torch.Generator(device="cuda").manual_seed(23)
+    A = torch.rand((n, n), generator=g, device="cuda") * 2 - 1
+    d = A.clone()
+    plan = qr.TilePlan(n, n, b)
+    plan.factor(d.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    R = torch.triu(d.t().double())
+    R64 = torch.linalg.qr(A.t().double(), mode="r").R
+    s = torch.sign(torch.diagonal(R64)) * torch.sign(torch.diagonal(R))
+    assert (torch.max(torch.abs(R - s[:, None] * R64)) / torch.max(torch.abs(R64))).item() <= 1e-4
+    back, orth = probe_accuracy(torch, plan, d, A, n, n, 128)
+    assert back <= 5 and orth <= 5, (back, orth)
+    plan.close()
