@@ -131,17 +131,34 @@ __global__ void __launch_bounds__(BQ * 32, 2) batched_tiledqr_kernel(const Batch
 // pass (every warp FFMA-bound at once), a barrier.  No warp ever waits for another one's data: the panel tiles, their
 // tau and the trailing tiles of a problem are written and read back by the same threads.  Same four tile kernels, same
 // operation order per tile and same output layout as cudaQRTask on each problem (bit-identical: bench.py checks it).
-constexpr int BW_FLOATS = 1088 + 1024 + 1024 + 32 + 64;         // Rs / V tile, top row of column 0 (V2 out while a panel), top row of column 1, tau, slots
+constexpr int BW_FLOATS = 1088 + 1024 + 1024 + 1024 + 64 + 64;   // Rs / V tile A, V tile B, top row of column 0 (V2 out while a panel), of column 1, tau x 2, slots
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// this lane's 128-byte column of a tile, global -> shared, asynchronously (LDGSTS); wait with cp_async_wait_all
+__device__ __forceinline__ void cp_async_col(float *dst_smem, const float *src_gmem)
+{
+    const uint32_t d = smem_u32(dst_smem);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16 * i), "l"(src_gmem + 4 * i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// Every warp of the CTA does the same work at the same time, so a warp that waits for a tile waits together with all
+// the others: nothing hides a synchronous load (first version, 12 warps, loads in front of every tile: 12.8 ms for
+// 10 000 x 256^2, issue slots 44 % busy, 0.7 warps per issue stalled on the long scoreboard;
+// profiles/r2_batched_warp_summary.txt).  Hence the software pipeline: the NEXT tile of a chain is requested before
+// the current one is worked on -- trailing tiles into registers (eight warps leave 255 registers per thread), the next
+// reflector tile by cp.async into the other half of a double buffer.
 template <int BW>                                               // warps = problems in flight per CTA
 __global__ void __launch_bounds__(BW * 32, 1) batched_warp_kernel(const BatchArgs a)
 {
     extern __shared__ __align__(16) float bsm[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *Vs = bsm + w * BW_FLOATS;
-    float *top0 = Vs + 1088, *top1 = top0 + 1024, *ts = top1 + 1024, *xs = ts + 32;
+    float *Vs = bsm + w * BW_FLOATS;                            // Rs (33-float rows) while this warp is a panel
+    float *VsB = Vs + 1088;
+    float *top0 = VsB + 1024, *top1 = top0 + 1024, *ts = top1 + 1024, *xs = ts + 64;
     const int p = a.p, q = a.q, K = p < q ? p : q, ldm = a.ldm;
     // the problems are dealt to the CTAs evenly up front (no tail of one late CTA); a CTA takes its share BW at a time
     const int per = a.nprob / (int)gridDim.x, rem = a.nprob % (int)gridDim.x;
@@ -156,10 +173,10 @@ __global__ void __launch_bounds__(BW * 32, 1) batched_warp_kernel(const BatchArg
         auto tile = [&](int I, int J) { return M + (size_t)(J * TB + lane) * ldm + I * TB; };
         for (int k = 0; k < K; ++k) {
             if (live) {
-                // ---- panel of step k: GEQRT + TSQRT chain (qrdecomp.c:532-557, 689-721)
-                float x[TB];
+                // ---- panel of step k: GEQRT + TSQRT chain (qrdecomp.c:532-557, 689-721); tile i + 1 is in flight during tile i
+                float x[TB], nx[TB];
                 load_col_gmem(x, tile(k, k));
-                if (k + 1 < p) prefetch_l2(tile(k + 1, k));
+                if (k + 1 < p) load_col_gmem(nx, tile(k + 1, k));
                 float t = geqrt_warp(x, xs, lane);
                 store_col_gmem(tile(k, k), x);
                 tb[((size_t)k * p + k) * TB + lane] = t;
@@ -167,8 +184,9 @@ __global__ void __launch_bounds__(BW * 32, 1) batched_warp_kernel(const BatchArg
                 for (int r = 0; r < TB; ++r) Vs[r * 33 + lane] = x[r];
                 __syncwarp();
                 for (int i = k + 1; i < p; ++i) {
-                    load_col_gmem(x, tile(i, k));
-                    if (i + 1 < p) prefetch_l2(tile(i + 1, k));
+#pragma unroll
+                    for (int r = 0; r < TB; ++r) x[r] = nx[r];
+                    if (i + 1 < p) load_col_gmem(nx, tile(i + 1, k));
                     float ti = tsqrt_warp(x, Vs, xs, top0, lane);
                     store_col_gmem(tile(i, k), x);
                     tb[((size_t)k * p + i) * TB + lane] = ti;
@@ -180,33 +198,44 @@ __global__ void __launch_bounds__(BW * 32, 1) batched_warp_kernel(const BatchArg
             }
             __syncthreads();
             if (live) {
-                // ---- step k applied to the trailing tile columns, two at a time (qrdecomp.c:620-644, 736-762)
+                // ---- step k applied to the trailing tile columns, two at a time (qrdecomp.c:620-644, 736-762).
+                // Items of a column pair: row k (UNMQR, the diagonal tile's reflectors), then rows k+1 .. p-1 (TSMQR).
+                // While item i is applied, item i + 1 is on its way: its reflector tile by cp.async into the other
+                // V buffer, its tau and its two trailing tiles into registers.
                 for (int j = k + 1; j < q; j += 2) {
                     const bool two = j + 1 < q;
-                    float x0[TB], x1[TB];
-                    auto stage_v = [&](int i) {              // reflector tile (i, k) and its tau -> shared memory
-                        load_col_gmem(x0, tile(i, k));       // (this thread wrote this very column in the panel phase)
-                        store_col_smem(Vs + lane * TB, x0);
-                        ts[lane] = tb[((size_t)k * p + i) * TB + lane];
-                        __syncwarp();
-                    };
-                    stage_v(k);
-                    load_col_gmem(x0, tile(k, j));
-                    if (two) load_col_gmem(x1, tile(k, j + 1));
-                    if (two) apply_reflectors_nc<2, false>(x0, x1, nullptr, nullptr, 0, Vs, ts);
-                    else apply_reflectors_nc<1, false>(x0, x0, nullptr, nullptr, 0, Vs, ts);
+                    float x0[TB], x1[TB], n0[TB], n1[TB];
+                    float ntau;
+                    __syncwarp();
+                    cp_async_col(Vs + lane * TB, tile(k, k));           // (this thread wrote this very column in the panel phase)
+                    ntau = tb[((size_t)k * p + k) * TB + lane];
+                    load_col_gmem(n0, tile(k, j));
+                    if (two) load_col_gmem(n1, tile(k, j + 1));
+                    for (int i = k; i < p; ++i) {
+                        float *vcur = ((i - k) & 1) ? VsB : Vs, *vnext = ((i - k) & 1) ? Vs : VsB;
+                        float *tcur = ts + ((i - k) & 1) * 32;
 #pragma unroll
-                    for (int r = 0; r < TB; ++r) { top0[r * TB + lane] = x0[r]; if (two) top1[r * TB + lane] = x1[r]; }
-                    for (int i = k + 1; i < p; ++i) {
-                        __syncwarp();                        // everyone is done with the previous reflector tile
-                        stage_v(i);
-                        load_col_gmem(x0, tile(i, j));
-                        if (two) load_col_gmem(x1, tile(i, j + 1));
-                        if (i + 1 < p) { prefetch_l2(tile(i + 1, k)); prefetch_l2(tile(i + 1, j)); if (two) prefetch_l2(tile(i + 1, j + 1)); }
-                        if (two) apply_reflectors_nc<2, true>(x0, x1, top0 + lane, top1 + lane, TB, Vs, ts);
-                        else apply_reflectors_nc<1, true>(x0, x0, top0 + lane, top0 + lane, TB, Vs, ts);
-                        store_col_gmem(tile(i, j), x0);
-                        if (two) store_col_gmem(tile(i, j + 1), x1);
+                        for (int r = 0; r < TB; ++r) { x0[r] = n0[r]; x1[r] = n1[r]; }
+                        tcur[lane] = ntau;
+                        cp_async_wait_all();
+                        __syncwarp();                                    // reflector tile i and its tau are in shared memory
+                        if (i + 1 < p) {
+                            cp_async_col(vnext + lane * TB, tile(i + 1, k));
+                            ntau = tb[((size_t)k * p + i + 1) * TB + lane];
+                            load_col_gmem(n0, tile(i + 1, j));
+                            if (two) load_col_gmem(n1, tile(i + 1, j + 1));
+                        }
+                        if (i == k) {
+                            if (two) apply_reflectors_nc<2, false>(x0, x1, nullptr, nullptr, 0, vcur, tcur);
+                            else apply_reflectors_nc<1, false>(x0, x0, nullptr, nullptr, 0, vcur, tcur);
+#pragma unroll
+                            for (int r = 0; r < TB; ++r) { top0[r * TB + lane] = x0[r]; if (two) top1[r * TB + lane] = x1[r]; }
+                        } else {
+                            if (two) apply_reflectors_nc<2, true>(x0, x1, top0 + lane, top1 + lane, TB, vcur, tcur);
+                            else apply_reflectors_nc<1, true>(x0, x0, top0 + lane, top0 + lane, TB, vcur, tcur);
+                            store_col_gmem(tile(i, j), x0);
+                            if (two) store_col_gmem(tile(i, j + 1), x1);
+                        }
                     }
                     __syncwarp();
 #pragma unroll
@@ -526,7 +555,7 @@ static int batched_launch(float *dA, int m, int n, int ldm, long long strideA, i
     a.A = dA; a.strideA = strideA; a.ldm = ldm; a.p = m / TB; a.q = n / TB; a.nprob = nprob;
     a.tauc = dTau; a.counter = dCounter;
     const char *force = getenv("QRB200_BATCHED");           // "colwarp" / "warp": A/B runs
-    const bool few = nprob < 4 * sms;                        // too few problems to give every warp of the device one
+    const bool few = nprob < 2 * sms;                        // too few problems to give the warps of the device one each
     if ((few && !(force && force[0] == 'w')) || (force && force[0] == 'c')) {
         // one CTA per problem, warp w = tile column w: more parallelism inside a problem (the tree levels of the TSQR)
         const int smem = BQ * WARP_FLOATS * (int)sizeof(float);
@@ -537,19 +566,11 @@ static int batched_launch(float *dA, int m, int n, int ldm, long long strideA, i
         CKB(cudaMemsetAsync(dCounter, 0, sizeof(int), stream));
         batched_tiledqr_kernel<<<nprob < grid_cap ? nprob : grid_cap, BQ * 32, smem, stream>>>(a);
     } else {
-        // twelve warps: 168 registers per thread, no spills -- 12.8 ms for 10 000 x 256^2 on B200; sixteen: 128 registers,
-        // 136 bytes of spills in the update phase -- 17.2 ms (round 1's kernel above: 18.1 ms with the round-2 panel kernels)
-        int bw = 12;
-        if (const char *e = getenv("QRB200_BATCHED_WARPS")) { const int v = atoi(e); if (v == 12 || v == 16) bw = v; }
-        const int smem = bw * BW_FLOATS * (int)sizeof(float);
+        // eight warps per CTA: 255 registers per thread hold the tile being worked on and the prefetched next one
+        const int smem = 8 * BW_FLOATS * (int)sizeof(float);
         const int grid = nprob < sms ? nprob : sms;
-        if (bw == 16) {
-            CKB(cudaFuncSetAttribute(batched_warp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            batched_warp_kernel<16><<<grid, 16 * 32, smem, stream>>>(a);
-        } else {
-            CKB(cudaFuncSetAttribute(batched_warp_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            batched_warp_kernel<12><<<grid, 12 * 32, smem, stream>>>(a);
-        }
+        CKB(cudaFuncSetAttribute(batched_warp_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        batched_warp_kernel<8><<<grid, 8 * 32, smem, stream>>>(a);
     }
     CKB(cudaGetLastError());
     return B200QR_OK;

@@ -499,7 +499,9 @@ tiledqr_persistent(const __grid_constant__ KernelArgs KA)
     __syncthreads();
 
     // panel warps: the last NPW warps of a CTA that runs both roles; the first NPW_SPLIT warps of a panel-only CTA
-    const int pw = split ? (panel_cta && warp < NPW_SPLIT ? warp : -1) : (warp >= W_PANEL ? warp - W_PANEL : -1);
+    // (the 1-column variant keeps its panel region behind the sweep stages, sized for NPW warps, whatever the roles)
+    constexpr int NPS = NC == 2 ? NPW_SPLIT : NPW;
+    const int pw = split ? (panel_cta && warp < NPS ? warp : -1) : (warp >= W_PANEL ? warp - W_PANEL : -1);
     if (pw >= 0) {
         uint32_t phbits = 0;
         for (;;) {

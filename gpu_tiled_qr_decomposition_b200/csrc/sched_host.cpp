@@ -10,7 +10,7 @@
 //   DAPP (l> k, m> k)  needs prog[l][m]   == k  and prog[l][k]   >= k+1 and prog[l-1][m] >= k+1
 // (gridscheduler.c:112-174 candoQRS/SAPP/QRD/DAPP).  Driven by one serial worker with the
 // reference's pick rule (gridscheduler.c:259-300) it reproduces the reference's task
-// sequence; tests/test_sched.py checks that against the golden traces.
+// sequence; tests/test_abi.py checks that against the golden traces.
 #include "../../include/qrb200.h"
 
 #include <cstdlib>
