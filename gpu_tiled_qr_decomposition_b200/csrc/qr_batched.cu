@@ -501,6 +501,14 @@ __global__ void __launch_bounds__(256, MINB) tsqr_strip_kernel(const StripArgs a
 // two-barrier form in which the next owner broadcasts its column before its scalar work (56.9 ms against 48.0 ms at
 // 4 194 304 x 256) and a form with eight reflectors per barrier and a compact-WY sweep by the other warps (58.9 ms).
 
+// Round 2 tried a second mapping for this kernel -- four matrix columns per thread, n / 4 threads per strip, the
+// broadcast column read once into registers for all four (8x less shared-memory traffic per FMA), four strips per SM --
+// and measured it slower (profiles/r2_measurements.md): 47.1 ms for the strip kernel alone against 42 ms, because with
+// 592 strips the triangles (78 MB) no longer stay in L2 while 8.6 GB of matrix stream past (ncu: 21.6 GB of DRAM writes
+// per launch = the 4.3 GB of reflectors + every R store, 131 KB per 32-row block; an L2 persisting window changed
+// nothing), and its pairwise levels took 0.92 ms each against 0.55 ms.  Removed; the kernel above is the engine.
+
+
 // ---- exchange step of the multi-GPU TSQR over peer memory (b200qr_tsqr_dist_*): flags are epoch numbers, monotonic
 __global__ void tsqr_signal_kernel(int *const *peer_flags, int world, int rank, int epoch)
 {
