@@ -333,7 +333,7 @@ def extra_batched(torch, q, L, fp32_tf, peaks, peak_src, steps, nprob=10000, m=2
     return {"workload": "batched %d x (%dx%d), tile size 32, reference layout per problem, 1 GPU" % (nprob, m, n),
             "ms": ms, "value": flops / ms * 1e-6, "unit": "GFLOP/s", "gram_rel_err_max_of_16": max(errs),
             "problem0_equals_single_matrix_path": same,
-            "roofline": roofline_hbm("batched_tiledqr_kernel", "%dx%dx%d" % (nprob, m, n), 8.0 * nprob * m * n, flops, ms,
+            "roofline": roofline_hbm("batched_warp_kernel", "%dx%dx%d" % (nprob, m, n), 8.0 * nprob * m * n, flops, ms,
                                      fp32_tf, peaks, peak_src)}
 
 

@@ -1,9 +1,10 @@
 set -x
 mkdir -p gpurun_out
-for rb in 32 16; do
-  QRB200_TSQR_RB=$rb python bench.py --only extras --extras tsqr --no-cpu --steps 5 > gpurun_out/s9_tsqr_v4_rb$rb.log 2>&1
-  QRB200_TSQR_NOPERSIST=1 QRB200_TSQR_RB=$rb python bench.py --only extras --extras tsqr --no-cpu --steps 5 > gpurun_out/s9_tsqr_v4_rb${rb}_nopersist.log 2>&1
+for n in 16384 32768; do
+  python tools/tc3_time.py $n 3 > gpurun_out/s11_tc3_new_$n.log 2>&1
+  QRB200_LIB=$PWD/oldlib/libqrb200_head.so python tools/tc3_time.py $n 3 > gpurun_out/s11_tc3_head_$n.log 2>&1
 done
-M="dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum"
-ncu --metrics $M --clock-control none --csv --log-file gpurun_out/s9_ncu_tsqr.csv -k regex:"tsqr_strip" python bench.py --only extras --extras tsqr --no-cpu --steps 1 > gpurun_out/s9_ncu_tsqr.out 2>&1
-timeout 600 python -m pytest tests/test_gpu_batched.py -m gpu -q -k tsqr > gpurun_out/s9_pytest.log 2>&1
+python tools/tc3_time.py 8192 3 > gpurun_out/s11_tc3_new_8192.log 2>&1
+QRB200_LIB=$PWD/oldlib/libqrb200_head.so python tools/tc3_time.py 8192 3 > gpurun_out/s11_tc3_head_8192.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_tc.py -m gpu -q > gpurun_out/s11_pytest.log 2>&1
+cat gpurun_out/s11_tc3_*.log
