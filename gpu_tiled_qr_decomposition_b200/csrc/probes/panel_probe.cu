@@ -103,3 +103,67 @@ extern "C" int b200qr_probe_panel(int nwarps, int busy, int reps, long long *cyc
     cudaFree(din); cudaFree(dout); cudaFree(dc); cudaFree(dstop);
     return rc;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// Update-kernel rate on one SM: 16 / NC warps, every thread NC columns of a tile row of 16 tiles, the reflector block,
+// tau and the resident top row in shared memory (no tile traffic: the pure rate of the inner loop of the sweep
+// consumers).  cycles[0] = SM cycles per tile row (16 tiles x 32 reflectors).
+namespace qrb200 {
+template <int NC>
+__global__ void __launch_bounds__(512 / NC) sweep_probe_kernel(long long *cycles, float *sink, int iters)
+{
+    extern __shared__ __align__(16) float ssm[];
+    float *vs = ssm, *ts = vs + TB * TB, *top = ts + TB;          // top: 32 rows x 512 columns
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int e = threadIdx.x; e < TB * TB; e += blockDim.x) vs[e] = 0.001f * (float)((e * 7) % 13 - 6);
+    if (threadIdx.x < TB) ts[threadIdx.x] = 1.0f + 0.01f * threadIdx.x;
+    for (int e = threadIdx.x; e < TB * 512; e += blockDim.x) top[e] = 0.01f * (float)(e % 17);
+    __syncthreads();
+    float b[NC][TB];
+    float *tp[NC];
+#pragma unroll
+    for (int n = 0; n < NC; ++n) {
+        tp[n] = top + (n * (16 / NC) + w) * TB + lane;
+#pragma unroll
+        for (int r = 0; r < TB; ++r) b[n][r] = 0.01f * (float)((r + lane + n) % 9);
+    }
+    float *tpc_[NC];
+#pragma unroll
+    for (int n = 0; n < NC; ++n) tpc_[n] = tp[n];
+    float *const (&tpc)[NC] = tpc_;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) apply_reflectors_cols<NC, true>(b, tpc, 512, vs, ts);
+    const long long t1 = clock64();
+    float acc = 0.f;
+#pragma unroll
+    for (int n = 0; n < NC; ++n)
+#pragma unroll
+        for (int r = 0; r < TB; ++r) acc += b[n][r];
+    if (acc == 123.456f) sink[0] = acc;
+    if (threadIdx.x == 0) cycles[0] = (t1 - t0) / iters;
+}
+}  // namespace qrb200
+
+extern "C" int b200qr_probe_sweep(int nc, int iters, long long *cycles)
+{
+    using namespace qrb200;
+    if (!cycles || iters <= 0 || (nc != 1 && nc != 2 && nc != 4)) return -1;
+    long long *dc = nullptr;
+    float *ds = nullptr;
+    if (cudaMalloc(&dc, 8) || cudaMalloc(&ds, 4)) return -2;
+    const int smem = (TB * TB + TB + TB * 512) * (int)sizeof(float);
+    int rc = 0;
+    auto run = [&](auto kern, int threads) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) { rc = -2; return; }
+        kern<<<1, threads, smem>>>(dc, ds, iters);
+        if (cudaDeviceSynchronize() != cudaSuccess) rc = -2;
+    };
+    if (nc == 1) run(sweep_probe_kernel<1>, 512);
+    else if (nc == 2) run(sweep_probe_kernel<2>, 256);
+    else run(sweep_probe_kernel<4>, 128);
+    if (rc == 0) cudaMemcpy(cycles, dc, 8, cudaMemcpyDeviceToHost);
+    cudaFree(dc); cudaFree(ds);
+    return rc;
+}

@@ -394,6 +394,100 @@ __device__ __forceinline__ float geqrt_warp(float (&a)[TB], float *xs, int lane)
     return my_tau;
 }
 
+// ------------------------------------------------------------------ a1: GEQRT, compact code (tensor-core engine)
+// Same kernel as geqrt_warp in a seventh of the code: four phases of eight reflectors.  Inside phase P the rows above 8P are finished and are skipped at compile time,
+// the rows from 8P + 8 on are always below the diagonal and need no mask; only the eight rows of the phase carry a
+// run-time mask (r > c).  So the passes over a column shrink with the phase (20 rows on average instead of 32 with 96
+// selects per reflector), the dot product runs against the UNSCALED column (its scale 1/piv goes onto the scalar, off
+// the rsqrt / rcp chain, as in TSQRT) and the sub-column sum of squares the next owner needs comes out of the update
+// pass.  Why it exists: geqrt_warp is 72 KB of straight-line code.  In the probe, the SIMT engine and the batched kernel
+// that is the fastest form (10.3k cycles per tile; this one: 24k), but inside the tensor-core kernel, whose panel CTAs
+// also run the T builders, it missed the instruction cache on every panel -- 22 us per GEQRT at 8192^2 and 48 us at
+// 16384^2 in the device trace, against 13 / 17 us for this form (tools/trace_timeline.py n 2).
+template <int P8>
+__device__ __forceinline__ void geqrt_phase(float (&a)[TB], float *xs, int lane, float &ssq_next, float &my_tau)
+{
+    constexpr int R0 = 8 * P8;                                 // first row this phase still touches
+#pragma unroll 1
+    for (int cc = 0; cc < 8; ++cc) {
+        const int c = R0 + cc;
+        float *slot = xs + (c & 1) * TB;
+        if (lane == c) {
+#pragma unroll
+            for (int r = R0; r < TB; r += 4) *reinterpret_cast<float4 *>(slot + r) = make_float4(a[r], a[r + 1], a[r + 2], a[r + 3]);
+        }
+        const float ssq_c = __shfl_sync(FULL, ssq_next, c);
+        __syncwarp();
+        float x[TB];
+#pragma unroll
+        for (int r = R0; r < TB; r += 4) {
+            const float4 t = *reinterpret_cast<const float4 *>(slot + r);
+            x[r] = t.x; x[r + 1] = t.y; x[r + 2] = t.z; x[r + 3] = t.w;
+        }
+        const HouseScalars h = house_scalars(slot[c], ssq_c);
+        // d = sum_{r > c} a[r] x[r]: the eight rows of the phase masked, the rest below the diagonal for every c of the phase
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, ac = 0.f;
+#pragma unroll
+        for (int r = R0; r < R0 + 8; r += 2) {
+            d0 = r > c ? fmaf(a[r], x[r], d0) : d0;
+            d1 = r + 1 > c ? fmaf(a[r + 1], x[r + 1], d1) : d1;
+            ac = r == c ? a[r] : (r + 1 == c ? a[r + 1] : ac);
+        }
+#pragma unroll
+        for (int r = R0 + 8; r < TB; r += 4) {
+            d0 = fmaf(a[r], x[r], d0); d1 = fmaf(a[r + 1], x[r + 1], d1);
+            d2 = fmaf(a[r + 2], x[r + 2], d2); d3 = fmaf(a[r + 3], x[r + 3], d3);
+        }
+        // A(:, j) -= tau v (v' A(:, j)),  v = [1; x / piv]:  f = tau (a_c + d / piv)
+        const float f = (lane >= c) ? h.tau * fmaf(h.inv, (d0 + d1) + (d2 + d3), ac) : 0.f;
+        const float g = (lane > c) ? -f * h.inv : 0.f;
+        const bool own = lane == c;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int r = R0; r < R0 + 8; r += 2) {
+            const float u0 = own ? x[r] * h.inv : fmaf(g, x[r], a[r]);          // the owner keeps the reflector
+            const float u1 = own ? x[r + 1] * h.inv : fmaf(g, x[r + 1], a[r + 1]);
+            a[r] = r > c ? u0 : (r == c ? a[r] - f : a[r]);
+            a[r + 1] = r + 1 > c ? u1 : (r + 1 == c ? a[r + 1] - f : a[r + 1]);
+            s2 = r > c + 1 ? fmaf(a[r], a[r], s2) : s2;                          // (lane c + 1 uses it: its column is not the owner's)
+            s3 = r + 1 > c + 1 ? fmaf(a[r + 1], a[r + 1], s3) : s3;
+        }
+#pragma unroll
+        for (int r = R0 + 8; r < TB; r += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[r + u] = own ? x[r + u] * h.inv : fmaf(g, x[r + u], a[r + u]);
+            // (row 8P + 8 is the NEXT diagonal row when this is the phase's last reflector: not below it)
+            s0 = (r > R0 + 8 || cc < 7) ? fmaf(a[r], a[r], s0) : s0;
+            s1 = fmaf(a[r + 1], a[r + 1], s1);
+            s2 = fmaf(a[r + 2], a[r + 2], s2); s3 = fmaf(a[r + 3], a[r + 3], s3);
+        }
+        ssq_next = (s0 + s1) + (s2 + s3);
+        if (own) my_tau = h.tau;
+    }
+}
+__device__ __forceinline__ float geqrt_warp_compact(float (&a)[TB], float *xs, int lane)
+{
+    float my_tau = 0.f;
+    float ssq = 0.f;                                           // sum_{r > 0} a[r]^2 (lane 0's is the one used)
+    {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int r = 1; r < TB; r += 4) {
+            s0 = fmaf(a[r], a[r], s0);
+            if (r + 1 < TB) s1 = fmaf(a[r + 1], a[r + 1], s1);
+            if (r + 2 < TB) s2 = fmaf(a[r + 2], a[r + 2], s2);
+            if (r + 3 < TB) s3 = fmaf(a[r + 3], a[r + 3], s3);
+        }
+        ssq = (s0 + s1) + (s2 + s3);
+    }
+    geqrt_phase<0>(a, xs, lane, ssq, my_tau);
+    geqrt_phase<1>(a, xs, lane, ssq, my_tau);
+    geqrt_phase<2>(a, xs, lane, ssq, my_tau);
+    geqrt_phase<3>(a, xs, lane, ssq, my_tau);
+    __syncwarp();
+    return my_tau;
+}
+
 // ------------------------------------------------------------------ a3/a4: UNMQR / TSMQR
 // Apply the 32 reflectors of one block to the column owned by this thread.
 //   vs  : reflector block in shared memory, reflector c at vs[c*32 .. c*32+31]
@@ -486,6 +580,45 @@ __device__ __forceinline__ void apply_reflectors_nc(float (&b0)[TB], float (&b1)
             if (HAS_TOP) top1[c * top_rs] = a0 - beta;
 #pragma unroll
             for (int r = 0; r < TB; ++r) b1[r] = fmaf(-beta, v[r], b1[r]);
+        }
+    }
+}
+
+// The same operation on N columns held by one thread, N a template parameter (round 2: N = 4).  What bounds the update
+// on the SIMT pipe is not FFMA issue but the shared-memory pipe: the reflector is the same for every thread, yet each
+// thread has to load it -- 8 broadcast LDS.128 per reflector and warp, four MIO cycles each -- so a warp with two
+// columns per thread spends 36 MIO cycles per 128 FFMA (ncu: mio_throttle / short_scoreboard on top, FMA pipe 34-42 %).
+// Four columns per thread halve the loads per FMA; the columns also give the FMA pipe four independent chains.
+template <int N, bool HAS_TOP>
+__device__ __forceinline__ void apply_reflectors_cols(float (&b)[N][TB], float *const (&top)[N], int top_rs, const float *vs,
+                                                      const float *ts)
+{
+#pragma unroll 2
+    for (int c = 0; c < TB; ++c) {
+        float v[TB];
+        load_col_smem(v, vs + c * TB);
+        if (!HAS_TOP) {
+#pragma unroll
+            for (int r = 0; r < TB; ++r) v[r] = (r > c) ? v[r] : ((r == c) ? 1.0f : 0.f);
+        }
+        const float tc = ts[c];
+        float a0[N], beta[N];
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+            a0[n] = HAS_TOP ? top[n][c * top_rs] : 0.f;
+            float d0 = a0[n], d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+            for (int r = 0; r < TB; r += 4) {
+                d0 = fmaf(b[n][r], v[r], d0); d1 = fmaf(b[n][r + 1], v[r + 1], d1);
+                d2 = fmaf(b[n][r + 2], v[r + 2], d2); d3 = fmaf(b[n][r + 3], v[r + 3], d3);
+            }
+            beta[n] = tc * ((d0 + d1) + (d2 + d3));
+        }
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+            if (HAS_TOP) top[n][c * top_rs] = a0[n] - beta[n];
+#pragma unroll
+            for (int r = 0; r < TB; ++r) b[n][r] = fmaf(-beta[n], v[r], b[n][r]);
         }
     }
 }

@@ -72,6 +72,7 @@ struct Params {
     int *prog_w[MAXW];              // tensor-core engine 3: every rank's progress words, writable (the builder warps push them)
     int npanel_ctas;          // > 0: role split -- CTAs [0, npanel_ctas) run only panel warps, the rest only sweeps;
                               // 0: every CTA runs both (small grids; NC = 1 only)
+    int panel_pairs;          // tensor-core engine: factor / builder warp pairs per panel CTA (2 or 4)
     int trace_mode;           // 1 = global sequence numbers, 2 = low 32 bits of %globaltimer (ns)
     int *trace;               // optional: 2 ints (start, finish) per tile task
     const long long *trace_off;  // K entries: first trace slot of step k
@@ -692,6 +693,7 @@ struct b200qr_plan_s {
     int nc;                 // matrix columns per consumer thread (1 or 2): kernel variant
     int G;                  // tile columns per sweep = distribution block
     int npanel_ctas;        // role split (0 = every CTA runs both roles)
+    int panel_pairs = 2;    // tensor-core engine: factor / builder pairs per panel CTA
     int nsweeps, npanels;   // tickets of this rank
     int rank = 0, world = 1;
     float *peer_A[MAXW];
@@ -865,7 +867,11 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
     if (engine == 2 && pl->nc != 5) return B200QR_EINVAL;          // the grid / shape cannot run the tensor-core engine
     if (pl->nc == 5) {
         // one sweep engine per CTA and SM; a panel CTA runs NPW5 factor / builder warp pairs
-        int want = (pl->npanel_ctas * NPW_SPLIT + tc3::NPW5 - 1) / tc3::NPW5;
+        // two pairs per panel CTA (factor warps on schedulers 0-1, builders on 2-3) and twice the panel CTAs: measured
+        // 23.9 / 132.6 / 996 ms at 8192^2 / 16384^2 / 32768^2 against 25.1 / 133.8 / 1014 ms with four pairs
+        pl->panel_pairs = 2;
+        if (const char *e = getenv("QRB200_PAIRS")) { const int v = atoi(e); if (v == 2 || v == 4) pl->panel_pairs = v; }
+        int want = (pl->npanel_ctas * NPW_SPLIT + pl->panel_pairs - 1) / pl->panel_pairs;
         if (const char *e = getenv("QRB200_NP")) { int v = *e ? atoi(e) : -1; if (v > 0 && v < grid) want = v; }
         pl->npanel_ctas = want < 1 ? 1 : want;
     }
@@ -952,7 +958,7 @@ static int fill_rank_ctx(RankCtx *rc, b200qr_plan_s *pl, float *dA, int ldm)
     P.tauc = pl->d_tauc; P.prog = pl->d_prog; P.ctr = pl->d_ctr;
     P.sweep_tab = pl->d_sweep_tab; P.nsweeps = pl->nsweeps; P.npanel_ctas = pl->npanel_ctas;
     P.panel_tab = pl->d_panel_tab; P.npanels = pl->npanels;
-    P.rank = pl->rank; P.world = pl->world;
+    P.rank = pl->rank; P.world = pl->world; P.panel_pairs = pl->panel_pairs;
     P.trace = (pl->trace && pl->trace != 3) ? pl->d_trace : nullptr; P.trace_off = pl->d_trace_off; P.trace_mode = pl->trace;
     if (getenv("QRB200_ONE_ENGINE")) P.trace_mode = 7;
     P.watchdog_ns = pl->watchdog_ns;

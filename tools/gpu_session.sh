@@ -1,9 +1,9 @@
 set -x
 mkdir -p gpurun_out
-nvidia-smi -L > gpurun_out/s10_gpus.log 2>&1
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
-timeout 500 $TR --master-port 29701 tools/dist_scan.py 32768 "-:-" "48:-" "128:-" "-:8" > gpurun_out/s10_scan8.log 2>&1
-timeout 400 $TR --master-port 29702 tools/dist_stress.py 8192 100 > gpurun_out/s10_stress8.log 2>&1
-timeout 900 $TR --master-port 29703 bench.py --gpus 8 --steps 2 --warmup 3 > gpurun_out/s10_bench8.log 2> gpurun_out/s10_bench8.err
-echo "bench rc $?" >> gpurun_out/s10_bench8.err
-grep -h "world\|stress" gpurun_out/s10_scan8.log gpurun_out/s10_stress8.log
+timeout 1500 python -m pytest tests -m gpu -q --maxfail=10 > gpurun_out/s15_pytest.log 2>&1
+echo "pytest rc $?" >> gpurun_out/s15_pytest.log
+for n in 8192 16384 32768; do python tools/tc3_time.py $n 3 > gpurun_out/s15_tc3_$n.log 2>&1; done
+python tools/tc3_time.py 8192 0 > gpurun_out/s15_simt_8192.log 2>&1
+python tools/trace_timeline.py 8192 2 > gpurun_out/s15_trace_8192.log 2>&1
+tail -3 gpurun_out/s15_pytest.log
+for f in gpurun_out/s15_tc3_*.log gpurun_out/s15_simt_8192.log; do echo "$f: $(tail -1 $f)"; done; grep "lag\|GEQRT" gpurun_out/s15_trace_8192.log

@@ -13,6 +13,9 @@ extern "C" {
  * cycles[2w + 1] = TSQRT of warp w; out3 (optional, 3 x 1024 floats) = warp 0's GEQRT tile, the triangle after its last
  * TSQRT and that TSQRT's V2, column-major (input: a fixed pseudo-random tile).  0 = ok. */
 int b200qr_probe_panel(int nwarps, int busy, int reps, long long *cycles, float *out3);
+/* SM cycles per tile row (16 tiles x 32 reflectors) of the SIMT update inner loop on one SM, nc = 1 / 2 / 4 matrix columns
+ * per thread (16 / nc warps), operands in shared memory: the rate the sweep consumers can reach at best.  0 = ok. */
+int b200qr_probe_sweep(int nc, int iters, long long *cycles);
 /* tcgen05 building-block check (csrc/probes/umma_probe.cu): hA 32 x 128 column-major, hV 32 x 32 column-major,
  * hW 128 x 32 row-major or NULL; hZ <- A^T V (128 x 32 row-major, 3xTF32 on the tensor cores);
  * hD2 <- A^T - W V^T when hW is given. */

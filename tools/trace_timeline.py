@@ -5,15 +5,40 @@ import numpy as np, torch
 import gpu_tiled_qr_decomposition_b200 as q
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+engine = int(sys.argv[2]) if len(sys.argv) > 2 else 0        # 0 auto, 1 SIMT, 2 tensor-core (panel tasks only are marked)
 torch.cuda.set_device(0)
 A = torch.rand((n, n), device="cuda") * 2 - 1
-plan = q.Plan(n, n, trace=2)
+plan = q.Plan(n, n, trace=2, engine=engine)
 for _ in range(2):
     d = A.clone()
     plan.factor(d.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
 tr = plan.read_trace().astype(np.int64)
-t0 = tr[:, 4].min()
+tr[:, 4:6] &= 0xffffffff                                  # low 32 bits of %globaltimer; unmarked tasks read 0xffffffff
+marked = tr[:, 4] != 0xffffffff
+t0 = tr[marked, 4].min()
+print("variant", plan.variant, "marked tasks", int(marked.sum()), "of", len(tr))
+if plan.variant == 5:
+    # tensor-core engine: only the panel tasks carry marks
+    p = n // 32
+    off = 0
+    starts, ends, geq, paces = [], [], [], []
+    for k in range(p):
+        cnt = (p - k) * (p - k)
+        col = tr[off:off + (p - k)]                        # j = k: rows k .. p-1
+        off += cnt
+        st = (col[:, 4] - t0) / 1e3; fi = (col[:, 5] - t0) / 1e3
+        starts.append(st[0]); ends.append(fi[-1]); geq.append(fi[0] - st[0])
+        if p - k > 3:
+            paces.append(np.median(np.diff(fi[1:])))
+    starts = np.array(starts); lag = np.diff(starts)
+    print("n", n, "span us %.1f" % max(ends))
+    print("lag between consecutive panel starts (us): median %.1f, p10 %.1f, p90 %.1f; sum %.0f us" % (
+        np.median(lag), np.percentile(lag, 10), np.percentile(lag, 90), lag.sum()))
+    print("GEQRT duration median %.2f us; TSQRT pace of a chain median %.2f us" % (np.median(geq), np.median(paces)))
+    for k in sorted(set([0, 1, 2, 8, 32, p // 4, p // 2, 3 * p // 4]) & set(range(p - 1))):
+        print("P(%3d): start %9.1f end %9.1f  lag to next %.1f" % (k, starts[k], ends[k], lag[k]))
+    sys.exit(0)
 p = n // 32
 span = (tr[:, 5].max() - t0) / 1e3
 print("n", n, "total span us %.1f" % span, "grid", plan.grid, "macro", plan.macro_tasks)
