@@ -997,7 +997,7 @@ static int reset_progress(b200qr_plan_s *pl, cudaStream_t stream, int fill = 0)
 static int launch(KernelArgs *ka, int nc, int grid, cudaStream_t stream)
 {
     void *args[] = {ka};
-    CK(cudaLaunchCooperativeKernel(kernel_of(nc, ka->rc[0].P.trace_mode == 3), dim3(grid), dim3(threads_of(nc)), args, smem_of(nc), stream));
+    CK(cudaLaunchCooperativeKernel(kernel_of(nc, ka->rc[0].P.trace_mode != 0), dim3(grid), dim3(threads_of(nc)), args, smem_of(nc), stream));
     return B200QR_OK;
 }
 
