@@ -139,13 +139,17 @@ __device__ __forceinline__ unsigned long long gtimer()
 struct Spin { unsigned n = 0; unsigned long long since = 0; };
 struct Watch {
     unsigned long long t0, limit;
+    // the slow path lives out of line: the waiting loops of the tensor-core engine's chain warps are the critical path
+    // of the whole factorisation and sensitive to every instruction compiled into them
+    __device__ __noinline__ void slow(Spin &s) const
+    {
+        const unsigned long long now = gtimer();
+        if (s.since == 0) s.since = now;
+        else if (now - s.since > limit) __trap();
+    }
     __device__ __forceinline__ void check(Spin &s) const
     {
-        if (((++s.n) & 0x3fffu) == 0) {
-            const unsigned long long now = gtimer();
-            if (s.since == 0) s.since = now;
-            else if (now - s.since > limit) __trap();
-        }
+        if (((++s.n) & 0x3fffu) == 0) slow(s);
     }
 };
 

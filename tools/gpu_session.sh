@@ -1,8 +1,9 @@
 set -x
 mkdir -p gpurun_out
-M="gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum"
-ncu --metrics $M --clock-control none --csv --log-file gpurun_out/s20_ncu_batched.csv -k regex:batched python bench.py --only extras --extras batched --no-cpu --steps 1 > gpurun_out/s20_ncu_batched.out 2>&1
-ncu --metrics $M --clock-control none --csv --log-file gpurun_out/s20_ncu_tsqr.csv -k regex:"tsqr_strip" python bench.py --only extras --extras tsqr --no-cpu --steps 1 > gpurun_out/s20_ncu_tsqr.out 2>&1
-ncu --set full --clock-control none --import-source on -k regex:batched_warp -c 1 -f -o gpurun_out/s20_batched python bench.py --only extras --extras batched --no-cpu --steps 1 > gpurun_out/s20_ncu_batched_full.out 2>&1
-ncu --set full --clock-control none --import-source on -k regex:tiledqr_persistent_tc3 -c 1 -f -o gpurun_out/s20_tc3_16384 python tools/tc3_time.py 16384 3 > gpurun_out/s20_ncu_tc3_full.out 2>&1
-ls -la gpurun_out/*.ncu-rep
+for rep in 1 2; do
+for n in 8192 16384 32768; do
+  python tools/tc3_time.py $n 3 > gpurun_out/s21_new_${n}_$rep.log 2>&1
+  QRB200_LIB=$PWD/oldlib/libqrb200_head.so python tools/tc3_time.py $n 3 > gpurun_out/s21_head_${n}_$rep.log 2>&1
+done
+done
+for f in gpurun_out/s21_*_*.log; do echo "$f: $(tail -1 $f)"; done
