@@ -91,6 +91,7 @@ def probe_lib():
         P = C.CDLL(PROBE_LIB_PATH)
         vp = C.c_void_p
         P.b200qr_probe_panel.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), vp]
+        P.b200qr_probe_dram_pattern.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
         P.b200qr_probe_sweep.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_longlong)]
         P.b200qr_probe_umma.argtypes = [vp, vp, vp, vp, vp]
         P.b200qr_probe_umma_mode.argtypes = [vp, vp, vp, vp, vp, C.c_int]

@@ -167,3 +167,60 @@ extern "C" int b200qr_probe_sweep(int nc, int iters, long long *cycles)
     cudaFree(dc); cudaFree(ds);
     return rc;
 }
+
+// ---------------------------------------------------------------------------------------------
+// DRAM access-pattern probe: one read + write pass over an n x n float32 matrix in the order the sweeps of the tensor-core
+// engine touch it (a group of four tile columns, tile row by tile row), warp = one 32 x 32 tile, lane = one 128-byte line.
+// packed = 0: column-major matrix, a tile's 32 lines are ld * 4 bytes apart (what the engine does today);
+// packed = 1: every tile contiguous (4 KB), tile (i, j) at (j * p + i) * 4 KB.
+namespace qrb200 {
+__global__ void __launch_bounds__(256) dram_pattern_kernel(float *A, int p, int q, long long ld, int packed, float add)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long ngroups = q / 4;
+    // work item = (group g, tile row i): four tiles; dealt to warps in sweep order (g-major, rows consecutive)
+    for (long long item = gw; item < ngroups * p; item += warps) {
+        const int g = (int)(item / p), i = (int)(item % p);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int j = 4 * g + t;
+            float *line = packed ? A + ((size_t)j * p + i) * 1024 + lane * 32 : A + (size_t)(j * 32 + lane) * ld + (size_t)i * 32;
+            float4 v[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[c] = __ldcs(reinterpret_cast<const float4 *>(line) + c);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { v[c].x += add; __stcs(reinterpret_cast<float4 *>(line) + c, v[c]); }
+        }
+    }
+}
+}  // namespace qrb200
+
+extern "C" int b200qr_probe_dram_pattern(int n, int packed, int ctas_per_sm, float *ms_out)
+{
+    using namespace qrb200;
+    if (n <= 0 || n % 128 || !ms_out) return -1;
+    float *A = nullptr;
+    if (cudaMalloc(&A, sizeof(float) * (size_t)n * n) != cudaSuccess) return -2;
+    cudaMemset(A, 0, sizeof(float) * (size_t)n * n);
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0, 0);
+        dram_pattern_kernel<<<sms * ctas_per_sm, 256>>>(A, n / 32, n / 32, n, packed, 1.0f);
+        cudaEventRecord(e1, 0);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(A); return -2; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(A);
+    *ms_out = best;
+    return 0;
+}

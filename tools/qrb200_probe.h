@@ -16,6 +16,9 @@ int b200qr_probe_panel(int nwarps, int busy, int reps, long long *cycles, float 
 /* SM cycles per tile row (16 tiles x 32 reflectors) of the SIMT update inner loop on one SM, nc = 1 / 2 / 4 matrix columns
  * per thread (16 / nc warps), operands in shared memory: the rate the sweep consumers can reach at best.  0 = ok. */
 int b200qr_probe_sweep(int nc, int iters, long long *cycles);
+/* One read + write pass over an n x n float32 matrix in the sweep order of the tensor-core engine (warp = tile, lane = one
+ * 128-byte line): packed = 0 column-major (lines ld*4 bytes apart), 1 = every 32 x 32 tile contiguous.  ms_out = best of 3. */
+int b200qr_probe_dram_pattern(int n, int packed, int ctas_per_sm, float *ms_out);
 /* tcgen05 building-block check (csrc/probes/umma_probe.cu): hA 32 x 128 column-major, hV 32 x 32 column-major,
  * hW 128 x 32 row-major or NULL; hZ <- A^T V (128 x 32 row-major, 3xTF32 on the tensor cores);
  * hD2 <- A^T - W V^T when hW is given. */
