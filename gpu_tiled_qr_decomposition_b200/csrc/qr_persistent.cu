@@ -1489,6 +1489,7 @@ void cudaQRTask(float *mat, int m, int n, int ldm, int maxblocks)
             const int orc = legacy_overlapped(mat, m, n, ldm, quiet);
             if (orc <= 0) {
                 if (env_on("QRB200_COMPAT_RESET")) { b200qr_release_cache(); cudaDeviceReset(); }
+                else if (const char *e = getenv("QRB200_CACHE")) { if (*e == '0') b200qr_release_cache(); }
                 return;
             }
         }
@@ -1508,6 +1509,7 @@ void cudaQRTask(float *mat, int m, int n, int ldm, int maxblocks)
                      cudaMemcpyDeviceToHost) != cudaSuccess)
         printf("copy back failed\n");
     if (env_on("QRB200_COMPAT_RESET")) { b200qr_release_cache(); cudaDeviceReset(); }   // gpucalc.cu:1685
+    else if (const char *e = getenv("QRB200_CACHE")) { if (*e == '0') b200qr_release_cache(); }   // like the reference: nothing kept between calls
 }
 
 void cudaQRFull(float *mat, int m, int n)
