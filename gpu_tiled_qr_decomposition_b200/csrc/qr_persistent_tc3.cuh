@@ -28,13 +28,26 @@
 
 namespace qrb200 {
 
+// Ring depths, overridable for A/B builds (-DTC3_NCI=4 ...).  Round-2 A/B at 16384^2 / 32768^2 (IN, OUT, operands):
+// (3,5,4) 132.6 / 1017 ms -- (4,5,3) 134.8 / 1035 -- (4,4,4) 144.8 / 1091 -- (5,4,3) 148.3 / 1108 -- (3,6,3) 134.4 / 1034:
+// the OUT ring is the one that matters and five stages are enough; releasing an OUT stage as soon as the TMA store has
+// READ it (wait_group.read) instead of at the row's publication changed nothing (132.4 / 1015).
+#ifndef TC3_NCI
+#define TC3_NCI 3
+#endif
+#ifndef TC3_NCO
+#define TC3_NCO 5
+#endif
+#ifndef TC3_NOS
+#define TC3_NOS 4
+#endif
 template <>
 struct Cfg<5> {
     static constexpr int G = 4;
     static constexpr int NS = 3;                                   // only places the panel warps' barriers (run_panel)
-    static constexpr int NCI = 3;                                  // IN ring: a tile row of the sweep as loaded
-    static constexpr int NCO = 5;                                  // OUT ring: a finished tile row for the storer
-    static constexpr int NOS = 4;                                  // operand rings (V, T, V^T: hi and lo tile each)
+    static constexpr int NCI = TC3_NCI;                                  // IN ring: a tile row of the sweep as loaded
+    static constexpr int NCO = TC3_NCO;                                  // OUT ring: a finished tile row for the storer
+    static constexpr int NOS = TC3_NOS;                                  // operand rings (V, T, V^T: hi and lo tile each)
     static constexpr int CSTAGE_BYTES = G * TILE_BYTES;
     static constexpr int OSTAGE_BYTES = 2 * TILE_BYTES;
     static constexpr int OFF_OUT = NCI * CSTAGE_BYTES;
