@@ -349,9 +349,10 @@ __device__ void sweep_loader(const Params &P, const CUtensorMap *mapA, const CUt
 
     for (int idx = 0; idx <= nrows; ++idx) {
         const int s = ring.stage;
-        mbar_wait_wd(cx.empty(s), ring.phase ^ 1, wd);
+        const int row = k + idx;
         if (idx < nrows) {
-            const int row = k + idx;
+            // The row's progress words are polled -- and the acquire fence paid -- BEFORE the wait for the stage: the
+            // words are monotonic, and the refill of a stage is on the consumers' clock (two stages), the poll is not.
             Spin spins;
             for (;;) {
                 bool ok = flag ? (flag_remote ? ld_relaxed_sys(flag + row) : ld_relaxed(flag + row)) >= target : true;
@@ -361,6 +362,9 @@ __device__ void sweep_loader(const Params &P, const CUtensorMap *mapA, const CUt
             }
             fence_acq_rel(remote);
             fence_proxy_async();
+        }
+        mbar_wait_wd(cx.empty(s), ring.phase ^ 1, wd);
+        if (idx < nrows) {
             if (lane == 0) mbar_arrive_expect_tx(cx.full(s), bytes);
             __syncwarp();
             if (active) tma_load_2d(cx.tile(s, lane), mapA, row * TB, jt * TB, cx.full(s));
@@ -388,17 +392,26 @@ __device__ void sweep_storer(const Params &P, const CUtensorMap *mapA, int k, in
         mbar_wait_wd(cx.computed(s), ring.phase, wd);
         if (idx > 0) {
             const int row = idx < nrows ? k + idx : k;           // last round writes the resident tile row k
+            // The stage goes back to the loader as soon as the stores have READ it; the row is published when they
+            // are complete.  (With two stages the refill of this stage must land while the consumers work on the
+            // other one: the store's completion and the publishing fence are ~2 us of that window.)
             if (active) {
                 tma_store_2d(mapA, row * TB, jt * TB, cx.tile(s, lane));
                 bulk_commit();
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(cx.empty(s));
+            if (active) {
                 bulk_wait_all();
                 __threadfence();
                 if (idx < nrows) trace_mark(P, k, row, jt, 1);
                 st_release(P.prog + (size_t)jt * p + row, k + 1);
             }
+        } else {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(cx.empty(s));
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(cx.empty(s));
         ring.advance<C::NS>();
     }
 }
