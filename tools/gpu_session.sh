@@ -1,13 +1,11 @@
 #!/bin/bash
-# A/B: SIMT sweep storer releases its stage after the store's read (new) vs after publication (base).
+# Round-end validation session: the GPU suite, smoke(), the default bench line and the reference arm.
+# Run on a B200 box:  gpurun --timeout 3600 -- 'bash tools/gpu_session.sh'
 mkdir -p gpurun_out
-T=gpurun_out/s29
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_dist.py tests/test_gpu_overlap.py -m gpu -q -x > ${T}_tests.log 2>&1; tail -2 ${T}_tests.log
-for rep in 1 2; do
-  for n in 8192 12288; do
-    QRB200_TC=0 timeout 300 python tools/tc3_time.py $n 0 2>&1 | sed 's/^/new  /' >> ${T}_ab.log
-    QRB200_TC=0 QRB200_LIB=$PWD/oldlib/libqrb200_st.so timeout 300 python tools/tc3_time.py $n 0 2>&1 | sed "s/^/stor /" >> ${T}_ab.log
-    QRB200_TC=0 QRB200_LIB=$PWD/oldlib/libqrb200_base.so timeout 300 python tools/tc3_time.py $n 0 2>&1 | sed "s/^/base /" >> ${T}_ab.log
-  done
-done
-cat ${T}_ab.log
+T=gpurun_out/s30
+timeout 2400 python -m pytest tests -m gpu -q -x > ${T}_tests.log 2>&1; echo "tests rc=$?" >> ${T}_tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > ${T}_smoke.log 2>&1
+timeout 900 python bench.py --steps 5 --warmup 3 > ${T}_bench.log 2>&1
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > ${T}_ref.log 2>&1
+timeout 300 python tools/trace_timeline.py 8192 > ${T}_trace8192.log 2>&1
+tail -3 ${T}_tests.log; tail -2 ${T}_smoke.log; tail -c 600 ${T}_bench.log; tail -15 ${T}_trace8192.log
