@@ -227,7 +227,7 @@ __device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int p
                 // readers poll with ld.relaxed.sys and fence at system scope on their side.)
                 bulk_wait_all();
                 __threadfence();
-                st_release(prog_col + pending, k + 1);
+                st_relaxed(prog_col + pending, k + 1);
             }
             pending = -1;
         }
@@ -266,8 +266,10 @@ __device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int p
             wait_ready(i);
             issue(i, s);
         }
-        bool have_next = false;
-        if (i + 1 < p && ready(i + 1)) { __threadfence(); issue(i + 1, s ^ 1); have_next = true; }
+        // The next tile's progress word is loaded here and looked at a quarter of the way through the TSQRT below, by
+        // lane 0, together with the publication of the previous tile: ONE fence then releases that tile's stores and
+        // acquires this word, and neither the word's L2 round trip nor a fence of its own sits on the chain.
+        int nf = i + 1 < p ? ld_relaxed(prog_col + i + 1) : -1;
         mbar_wait_wd(&pfull[s], (phbits >> s) & 1, wd); phbits ^= 1u << s;
         float b[TB];
         load_col_sw(b, pin0 + s * TB * TB, lane);
@@ -275,9 +277,24 @@ __device__ void run_panel(const Params &P, const CUtensorMap *mapA, int k, int p
         // V2 is assembled straight in a TMA output tile (two of them, alternating by row: the store
         // of the previous tile is still in flight and is published a quarter of the way through)
         float *pout = pout0 + (i & 1) * TB * TB;
-        float ti = tsqrt_warp_v<true>(b, Rs, xs, pout, lane, publish);
+        auto mid = [&]() {
+            nf = __shfl_sync(FULL, nf, 0);
+            const bool nxt = nf >= k;
+            if (lane == 0 && (pending >= 0 || nxt)) {
+                if (pending >= 0) bulk_wait_all();
+                __threadfence();
+                if (pending >= 0) st_relaxed(prog_col + pending, k + 1);
+                if (nxt) {
+                    fence_proxy_async();
+                    mbar_arrive_expect_tx(&pfull[s ^ 1], TILE_BYTES);
+                    tma_load_2d(pin0 + (s ^ 1) * TB * TB, mapA, (i + 1) * TB, k * TB, &pfull[s ^ 1]);
+                }
+            }
+            pending = -1;
+        };
+        float ti = tsqrt_warp_v<true>(b, Rs, xs, pout, lane, mid);
+        const bool have_next = nf >= k;
         if (lane == 0) trace_mark(P, k, i, k, 1);
-        publish();
         tauc[i * TB + lane] = ti;
         fence_proxy_async_smem();
         __syncwarp();                                // also orders this warp's tau stores before lane 0's release
