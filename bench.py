@@ -594,33 +594,38 @@ def run_b200_multi(args, rank, world, local_rank):
     torch.cuda.empty_cache()
     dist.barrier()
 
-    # ---- e2e: the owned tile columns travel pinned host -> device -> pinned host around the factorisation, one copy per
-    # contiguous run straight into / out of the rank's matrix (b200qr_copy = cudaMemcpy, synchronous)
-    run_bytes = [(j1 - j0) * 32 * m * 4 for j0, j1 in runs]
-    h_in = [A0[j0 * 32:j1 * 32].cpu().pin_memory() for j0, j1 in runs]
-    h_out = [torch.empty_like(x).pin_memory() for x in h_in]
+    # ---- e2e: b200qr_dist_reset_host / b200qr_dist_factor_host on pinned host memory -- the rank's kernel starts at once,
+    # its owned tile columns stream in behind it (progress words gate the step-0 tasks) and every finished block of
+    # columns streams back while the kernel works on the rest.  The host buffer holds the rank's columns only (packed).
+    h_in = torch.cat([A0[j0 * 32:j1 * 32] for j0, j1 in runs]).cpu().pin_memory()
+    h_work = torch.empty_like(h_in).pin_memory()
     e2e_steps = max(1, min(args.steps, 2))
     e2e_s = 0.0
+    e2e_same = True
     for it in range(e2e_steps + 1):
+        h_work.copy_(h_in)                                           # (host to host: restores the input, not timed)
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for (j0, j1), hb, nb in zip(runs, h_in, run_bytes):
-            q.check(L.b200qr_copy(C.c_void_p(rk.matrix_ptr + j0 * 32 * m * 4), C.c_void_p(hb.data_ptr()), nb))
-        rk.reset(stream)
-        dist.barrier()
-        rk.factor(stream)
-        torch.cuda.synchronize()
-        for (j0, j1), hb, nb in zip(runs, h_out, run_bytes):
-            q.check(L.b200qr_copy(C.c_void_p(hb.data_ptr()), C.c_void_p(rk.matrix_ptr + j0 * 32 * m * 4), nb))
+        rk.reset_host()
+        dist.barrier()                                               # every rank's words say "input not here yet"
+        rk.factor_host(h_work.data_ptr(), m, packed=True)
         dist.barrier()
         if it > 0:
             e2e_s += time.perf_counter() - t0
+    # the columns that came back are the ones the device-resident run produced
+    dchk = torch.empty((n, m), device="cuda", dtype=torch.float32)
+    rk.download(dchk.data_ptr())
+    e2e_same = bool(torch.equal(torch.cat([dchk[j0 * 32:j1 * 32] for j0, j1 in runs]).cpu(), h_work))
+    del dchk
+    same_t = torch.tensor([1 if e2e_same else 0], device="cuda")
+    dist.all_reduce(same_t, op=dist.ReduceOp.MIN)
+    e2e_same = bool(same_t.item())
     t = torch.tensor([e2e_s / e2e_steps], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = flops / t.item() * 1e-9
     variant, block, grid = rk.variant, rk.block, rk.grid
     rk.close()
-    del A0, h_in, h_out
+    del A0, h_in, h_work
     torch.cuda.empty_cache()
 
     peaks, peak_src = measured_peaks()
@@ -651,8 +656,9 @@ def run_b200_multi(args, rank, world, local_rank):
             "roofline": roofline,
             "cpu_baseline": None if args.no_cpu else cpu_baseline_obj(args.cpu_sample),
             "e2e": {"value": e2e_val, "unit": "GFLOP/s", "h2d_bytes_per_step": 4 * n * n, "d2h_bytes_per_step": 4 * n * n,
-                    "api": "b200qr_dist_* (C ABI): owned tile columns copied pinned host -> rank matrix -> pinned host, one "
-                           "cudaMemcpy per contiguous run of owned columns", "steps": e2e_steps},
+                    "api": "b200qr_dist_reset_host / b200qr_dist_factor_host (C ABI) on pinned host memory, one call per rank: "
+                           "the owned tile columns stream in behind the running kernel and finished blocks stream back "
+                           "while it works on the rest", "steps": e2e_steps, "equals_device_path": e2e_same},
             "gpu_launches": args.steps * world, "clocks": clocks,
             "check": {"gram_rel_err_owned_block_max": gram, "whole_matrix_vs_single_gpu": ident,
                       "backward_err_n_eps": back, "orthogonality_n_eps": orth, "bound_n_eps": 10.0}}

@@ -28,7 +28,7 @@ EXPORTS = (
     "b200qr_sched_rank_tickets_skew", "b200qr_sched_sweep_order_lag",
     "b200qr_dist_create", "b200qr_dist_destroy", "b200qr_dist_handle_bytes", "b200qr_dist_export",
     "b200qr_dist_connect", "b200qr_dist_matrix", "b200qr_dist_tau_device", "b200qr_dist_block",
-    "b200qr_dist_owner", "b200qr_dist_grid", "b200qr_dist_variant", "b200qr_dist_read_trace", "b200qr_dist_tile_tasks", "b200qr_dist_reset", "b200qr_dist_factor",
+    "b200qr_dist_owner", "b200qr_dist_grid", "b200qr_dist_variant", "b200qr_dist_read_trace", "b200qr_dist_tile_tasks", "b200qr_dist_reset", "b200qr_dist_factor", "b200qr_dist_reset_host", "b200qr_dist_factor_host",
     "b200qr_dist_connect_local", "b200qr_dist_factor_group",
     "b200qr_batched_workspace_floats", "b200qr_batched_factor", "b200qr_batched_last_cuda_error",
     "b200qr_tsqr_create", "b200qr_tsqr_create_streaming", "b200qr_tsqr_create_tiles", "b200qr_tsqr_leaves", "b200qr_tsqr_stream_block_rows", "b200qr_tsqr_create_rstack", "b200qr_tsqr_destroy", "b200qr_tsqr_levels", "b200qr_tsqr_factor",
@@ -167,6 +167,8 @@ def lib():
         L.b200qr_dist_tile_tasks.argtypes = [vp]
         L.b200qr_dist_tile_tasks.restype = C.c_long
         L.b200qr_dist_factor.argtypes = [vp, vp]
+        L.b200qr_dist_reset_host.argtypes = [vp]
+        L.b200qr_dist_factor_host.argtypes = [vp, vp, C.c_longlong, C.c_int, C.POINTER(C.c_float)]
         L.b200qr_dist_connect_local.argtypes = [C.POINTER(vp), C.c_int]
         L.b200qr_dist_factor_group.argtypes = [C.POINTER(vp), C.c_int, vp]
         L.b200qr_batched_workspace_floats.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
@@ -482,6 +484,18 @@ class DistRank:
 
     def factor(self, stream=0):
         check(lib().b200qr_dist_factor(self._h, C.c_void_p(stream)), "b200qr_dist_factor")
+
+    def reset_host(self):
+        """Progress words = 'input not here yet' (synchronous); barrier, then factor_host."""
+        check(lib().b200qr_dist_reset_host(self._h), "b200qr_dist_reset_host")
+
+    def factor_host(self, host_ptr, ldh, packed=False):
+        """Factor with HOST data (pinned), copies overlapped with the kernel; returns the kernel's milliseconds.
+        packed: host_ptr holds only this rank's tile columns, consecutively; else the whole m x n matrix."""
+        ms = C.c_float(0.0)
+        check(lib().b200qr_dist_factor_host(self._h, C.c_void_p(host_ptr), C.c_longlong(ldh), int(bool(packed)), C.byref(ms)),
+              "b200qr_dist_factor_host")
+        return ms.value
 
     def close(self):
         if self._h:

@@ -1089,12 +1089,33 @@ int b200qr_factor_device(b200qr_plan_t pl, float *dA, int ldm, void *stream_)
 }
 
 // ---------------------------------------------------------------- multi-GPU (one rank per process)
+// streams / events / pinned scratch of a rank's overlapped host path (b200qr_dist_factor_host), made on first use
+struct DistHost {
+    cudaStream_t ks = nullptr, hs = nullptr, ds = nullptr, ps = nullptr;   // kernel, host-to-device, device-to-host, polls
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int *h_zero = nullptr, *h_prog = nullptr;
+    bool pending = false;           // b200qr_dist_reset_host ran, b200qr_dist_factor_host has not yet
+};
 struct b200qr_dist_s {
     b200qr_plan_s plan;
     float *dA = nullptr;            // this rank's m x n matrix (ld = m); only the owned tile columns are used
     void *opened[4 * MAXW] = {};    // IPC mappings to close
     int connected = 0;
+    DistHost *host = nullptr;
 };
+static void dist_host_free(DistHost *h)
+{
+    if (!h) return;
+    if (h->ks) cudaStreamDestroy(h->ks);
+    if (h->hs) cudaStreamDestroy(h->hs);
+    if (h->ds) cudaStreamDestroy(h->ds);
+    if (h->ps) cudaStreamDestroy(h->ps);
+    if (h->e0) cudaEventDestroy(h->e0);
+    if (h->e1) cudaEventDestroy(h->e1);
+    if (h->h_zero) cudaFreeHost(h->h_zero);
+    if (h->h_prog) cudaFreeHost(h->h_prog);
+    delete h;
+}
 
 // what a rank tells the others: its buffers, and the plan facts every rank must agree on (the kernel variant fixes the
 // distribution block, so ranks with different variants would disagree on who owns which tile column)
@@ -1121,6 +1142,7 @@ int b200qr_dist_destroy(b200qr_dist_t d)
 {
     if (!d) return B200QR_EINVAL;
     for (void *ptr : d->opened) if (ptr) cudaIpcCloseMemHandle(ptr);
+    dist_host_free(d->host);
     plan_free(&d->plan);
     cudaFree(d->dA);
     delete d;
@@ -1245,6 +1267,133 @@ int b200qr_dist_factor_group(b200qr_dist_t *all, int world, void *stream_)
     for (int r = 0; r < world; ++r)
         if (ka.rc[r].P.npanel_ctas >= grid) return B200QR_EINVAL;
     return launch(&ka, all[0]->plan.nc, grid * world, stream);
+}
+
+// ---- a rank's factorisation with HOST data, copies overlapped with the kernel (the multi-GPU sibling of cudaQRTask's
+// overlapped path further down; the mechanism is described there).  Protocol, every rank:
+//     b200qr_dist_reset_host  ->  [barrier]  ->  b200qr_dist_factor_host  (returns when the rank's columns are back)
+// reset_host sets the rank's progress words to -1 = "this tile's input is not here yet" (synchronous, like
+// b200qr_dist_reset).  factor_host launches the rank's kernel, sends the OWNED tile columns in behind it in chunks, each
+// followed by zeros onto the chunk's words, polls the words of its blocks and copies every finished block back while
+// the kernel works on the rest.  Peers are not involved: they read this rank's reflector tiles / operand tiles only
+// behind the panel column's words, which move from -1 over 0 to k + 1 like in any other run.
+static bool column_final(const int *w, int j, int p, int q);
+constexpr int DH_MAXCHUNK = 16;      // tile columns per transfer, at most
+constexpr int DH_POLL = 4;           // owned blocks whose words one poll fetches
+
+static int dist_host_init(b200qr_dist_s *d)
+{
+    if (d->host) return B200QR_OK;
+    DistHost *h = new DistHost;
+    const int p = d->plan.p, G = d->plan.G;
+    bool ok = cudaStreamCreateWithFlags(&h->ks, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&h->hs, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&h->ds, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&h->ps, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreate(&h->e0) == cudaSuccess && cudaEventCreate(&h->e1) == cudaSuccess &&
+              cudaMallocHost(&h->h_zero, sizeof(int) * (size_t)DH_MAXCHUNK * p) == cudaSuccess &&
+              cudaMallocHost(&h->h_prog, sizeof(int) * (size_t)DH_POLL * G * p) == cudaSuccess;
+    if (!ok) { g_last_cuda = (int)cudaGetLastError(); dist_host_free(h); return B200QR_ECUDA; }
+    memset(h->h_zero, 0, sizeof(int) * (size_t)DH_MAXCHUNK * p);
+    d->host = h;
+    return B200QR_OK;
+}
+
+int b200qr_dist_reset_host(b200qr_dist_t d)
+{
+    if (!d) return B200QR_EINVAL;
+    int rc = dist_host_init(d);
+    if (rc != B200QR_OK) return rc;
+    rc = reset_progress(&d->plan, d->host->ks, 0xff);
+    if (rc != B200QR_OK) return rc;
+    CK(cudaStreamSynchronize(d->host->ks));
+    d->host->pending = true;
+    return B200QR_OK;
+}
+
+// h: host matrix, column-major, leading dimension ldh >= m.  packed = 0: the whole m x n matrix (only this rank's tile
+// columns are read and written); packed = 1: this rank's tile columns only, one after the other in increasing order.
+int b200qr_dist_factor_host(b200qr_dist_t d, float *h, long long ldh, int packed, float *kernel_ms)
+{
+    if (!d || !d->connected || !h || ldh < d->plan.m || !d->host || !d->host->pending) return B200QR_EINVAL;
+    DistHost &c = *d->host;
+    b200qr_plan_s *pl = &d->plan;
+    const int p = pl->p, q = pl->q, m = pl->m, G = pl->G, world = pl->world, rank = pl->rank;
+    c.pending = false;
+    long long ctl = (8ll << 20) / ((long long)m * TB * (long long)sizeof(float));
+    const int ct = ctl < 1 ? 1 : (ctl > DH_MAXCHUNK ? DH_MAXCHUNK : (int)ctl);
+    int rc_cuda = 0;
+    auto ck = [&](cudaError_t e) { if (e != cudaSuccess && !rc_cuda) { rc_cuda = (int)e; g_last_cuda = (int)e; } };
+    const int nblk_all = (q + G - 1) / G;
+    int nblk = 0;                                                       // owned blocks
+    for (int g = rank; g < nblk_all; g += world) ++nblk;
+    auto blk_j0 = [&](int b) { return (rank + b * world) * G; };        // first tile column of owned block b
+    auto blk_nt = [&](int b) { const int j0 = blk_j0(b); return q - j0 < G ? q - j0 : G; };
+    auto host_col = [&](int b, int j) {                                 // host address of tile column j of owned block b
+        const long long tc = packed ? (long long)b * G + (j - blk_j0(b)) : j;    // (only the last block can be short)
+        return h + (size_t)tc * TB * (size_t)ldh;
+    };
+    KernelArgs ka;
+    ka.nvirt = 1;
+    int rc = fill_rank_ctx(&ka.rc[0], pl, d->dA, m);
+    if (rc != B200QR_OK) return rc;
+    ck(cudaEventRecord(c.e0, c.ks));
+    rc = launch(&ka, pl->nc, pl->grid, c.ks);
+    ck(cudaEventRecord(c.e1, c.ks));
+    if (rc != B200QR_OK) { cudaStreamSynchronize(c.ks); return rc; }
+    // ---- in
+    for (int b = 0; b < nblk && !rc_cuda; ++b) {
+        const int j0 = blk_j0(b), nt = blk_nt(b);
+        for (int c0 = j0; c0 < j0 + nt; c0 += ct) {
+            const int n1 = j0 + nt - c0 < ct ? j0 + nt - c0 : ct;
+            ck(cudaMemcpy2DAsync(d->dA + (size_t)c0 * TB * m, sizeof(float) * m, host_col(b, c0), sizeof(float) * (size_t)ldh,
+                                 sizeof(float) * m, (size_t)n1 * TB, cudaMemcpyHostToDevice, c.hs));
+            ck(cudaMemcpyAsync(pl->d_prog + (size_t)c0 * p, c.h_zero, sizeof(int) * (size_t)n1 * p, cudaMemcpyHostToDevice, c.hs));
+        }
+    }
+    if (rc_cuda) {
+        // the kernels (ours and the peers') may wait for columns that will never arrive: release every owned word
+        for (int b = 0; b < nblk; ++b)
+            for (int c0 = blk_j0(b); c0 < blk_j0(b) + blk_nt(b); c0 += DH_MAXCHUNK) {
+                const int n1 = blk_j0(b) + blk_nt(b) - c0 < DH_MAXCHUNK ? blk_j0(b) + blk_nt(b) - c0 : DH_MAXCHUNK;
+                cudaMemcpyAsync(pl->d_prog + (size_t)c0 * p, c.h_zero, sizeof(int) * (size_t)n1 * p, cudaMemcpyHostToDevice, c.hs);
+            }
+        cudaStreamSynchronize(c.hs);
+        cudaStreamSynchronize(c.ks);
+        return B200QR_ECUDA;
+    }
+    // ---- out
+    auto copy_back = [&](int b) {
+        const int j0 = blk_j0(b), nt = blk_nt(b);
+        ck(cudaMemcpy2DAsync(host_col(b, j0), sizeof(float) * (size_t)ldh, d->dA + (size_t)j0 * TB * m, sizeof(float) * m,
+                             sizeof(float) * m, (size_t)nt * TB, cudaMemcpyDeviceToHost, c.ds));
+    };
+    int bdone = 0;
+    while (bdone < nblk && !rc_cuda) {
+        if (cudaEventQuery(c.e1) != cudaErrorNotReady) break;              // finished (or failed): the rest in one go
+        const int w = nblk - bdone < DH_POLL ? nblk - bdone : DH_POLL;
+        for (int i = 0; i < w; ++i)
+            ck(cudaMemcpyAsync(c.h_prog + (size_t)i * G * p, pl->d_prog + (size_t)blk_j0(bdone + i) * p,
+                               sizeof(int) * (size_t)blk_nt(bdone + i) * p, cudaMemcpyDeviceToHost, c.ps));
+        ck(cudaStreamSynchronize(c.ps));
+        int adv = 0;
+        for (; adv < w; ++adv) {
+            bool fin = true;
+            const int j0 = blk_j0(bdone + adv), nt = blk_nt(bdone + adv);
+            for (int t = 0; t < nt && fin; ++t) fin = column_final(c.h_prog + ((size_t)adv * G + t) * p, j0 + t, p, q);
+            if (!fin) break;
+        }
+        if (adv > 0) { for (int i = 0; i < adv; ++i) copy_back(bdone + i); bdone += adv; }
+        else usleep(50);
+    }
+    (void)cudaGetLastError();                                              // cudaErrorNotReady of the queries
+    cudaError_t se = cudaEventSynchronize(c.e1);
+    if (se != cudaSuccess) { g_last_cuda = (int)se; cudaStreamSynchronize(c.hs); return se == cudaErrorLaunchFailure ? B200QR_ESTALL : B200QR_ECUDA; }
+    for (; bdone < nblk; ++bdone) copy_back(bdone);
+    ck(cudaStreamSynchronize(c.hs));
+    ck(cudaStreamSynchronize(c.ds));
+    if (kernel_ms) { float ms = 0.f; cudaEventElapsedTime(&ms, c.e0, c.e1); *kernel_ms = ms; }
+    return rc_cuda ? B200QR_ECUDA : B200QR_OK;
 }
 
 int b200qr_tau_to_reference(b200qr_plan_t pl, float *dTauMat, int ldtau, void *stream_)

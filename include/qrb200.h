@@ -140,6 +140,16 @@ int    b200qr_dist_reset(b200qr_dist_t d, void *stream);
 int    b200qr_dist_factor(b200qr_dist_t d, void *stream);
 /* Same-process variants for rank objects that share ONE device (tests / fewer GPUs than ranks):
  * wire them with plain pointers and run all of them in a single cooperative launch (world <= 2). */
+/* A rank's factorisation with HOST data, the copies overlapped with the kernel (the multi-GPU sibling of cudaQRTask's
+ * overlapped path; the reference has no multi-GPU entry point).  Every rank: reset_host (progress words = "input not
+ * here yet"; synchronous) -> [barrier] -> factor_host, which launches the rank's kernel, streams the OWNED tile columns in
+ * behind it, copies every finished block of tile columns back while the kernel works on the rest, and returns when
+ * they are all back.  h: column-major host matrix (pinned for the overlap to happen), leading dimension ldh >= m;
+ * packed = 0: the whole m x n matrix, of which only this rank's tile columns are read and written; packed = 1: this
+ * rank's tile columns only, consecutive in increasing order.  kernel_ms (optional): the kernel's run time, which here
+ * includes waiting for its input. */
+int    b200qr_dist_reset_host(b200qr_dist_t d);
+int    b200qr_dist_factor_host(b200qr_dist_t d, float *h, long long ldh, int packed, float *kernel_ms);
 int    b200qr_dist_connect_local(b200qr_dist_t *all, int world);
 int    b200qr_dist_factor_group(b200qr_dist_t *all, int world, void *stream);
 

@@ -109,6 +109,34 @@ def test_ranks_must_agree_on_the_plan(cuda, qr):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("m,n,packed,engine", [(2048, 2048, False, 0), (4096, 3072, True, 0), (4096, 4096, True, 2), (1024, 4096, False, 0)])
+def test_rank_factor_host_overlapped_matches_device_path(cuda, qr, m, n, packed, engine):
+    """b200qr_dist_reset_host / b200qr_dist_factor_host (host data, copies overlapped with the kernel) on a one-rank
+    world: the matrix that comes back must be the device path's, bit for bit, in both host layouts."""
+    torch = cuda
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = torch.rand((n, m), generator=g, device="cuda", dtype=torch.float32) * 2 - 1      # row of the tensor = matrix column
+    plan = qr.Plan(m, n, engine=engine)
+    ref = A.clone()
+    s = torch.cuda.current_stream().cuda_stream
+    plan.factor(ref.data_ptr(), m, s)
+    torch.cuda.synchronize()
+    rk = qr.DistRank(m, n, 0, 1, engine=engine)
+    assert rk.variant == plan.variant
+    ldh = m + 32                                                       # a leading dimension of its own
+    for rep in range(2):                                               # the second call reuses streams and scratch
+        h = torch.zeros((n, ldh), dtype=torch.float32).pin_memory()
+        h[:, :m] = A.cpu()
+        rk.reset_host()
+        ms = rk.factor_host(h.data_ptr(), ldh, packed=packed)          # one rank owns everything: both layouts coincide
+        assert ms > 0
+        assert torch.equal(h[:, :m], ref.cpu())
+        assert float(h[:, m:].abs().max()) == 0.0                      # the padding of the host matrix is not touched
+    # protocol: factor_host without reset_host is refused
+    assert qr.lib().b200qr_dist_factor_host(rk._h, h.data_ptr(), ldh, 0, None) == -1
+    rk.close(); plan.close()
+
+
 def test_tensor_core_engine_on_two_real_gpus(cuda):
     """The multi-GPU form of the tensor-core engine (operand tiles broadcast by TMA stores into every rank's workspace)
     must give the single-GPU engine's result bit for bit.  Needs two visible GPUs (skipped on a one-GPU box)."""
@@ -127,6 +155,7 @@ def test_tensor_core_engine_on_two_real_gpus(cuda):
                        capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "single-GPU variant 5" in r.stdout and "identical: True" in r.stdout, r.stdout[-2000:]
+    assert "host identical: True" in r.stdout, r.stdout[-2000:]      # b200qr_dist_factor_host, copies overlapped
 
 
 def test_tsqr_split_over_two_real_gpus(cuda):
