@@ -120,8 +120,11 @@ int b200qr_factor_host(float *hA, int m, int n, int ldm, float *hTauMat, float *
  *
  * Protocol (all ranks):  create -> export -> [exchange the handle bytes, e.g. all_gather] ->
  * connect -> fill the owned columns of b200qr_dist_matrix() -> reset -> [barrier] -> factor ->
- * [stream sync].  Results (R and V of the owned tile columns, tau of the owned panels) stay in
- * the rank's matrix / tau buffer.                                                                */
+ * [stream sync] -> [barrier].  Results (R and V of the owned tile columns, tau of the owned panels)
+ * stay in the rank's matrix / tau buffer.  The closing barrier matters when the factorisation is
+ * repeated: until EVERY rank's kernel has finished, peers still read this rank's reflector tiles and
+ * progress words (SIMT engine) or still write operand tiles and panel progress words into this
+ * rank's buffers (tensor-core engine), so a rank must not refill its matrix or reset before it.   */
 typedef struct b200qr_dist_s *b200qr_dist_t;
 int    b200qr_dist_create(b200qr_dist_t *d, int m, int n, int rank, int world, const b200qr_opts *opts);
 int    b200qr_dist_destroy(b200qr_dist_t d);
@@ -147,7 +150,7 @@ int    b200qr_dist_factor(b200qr_dist_t d, void *stream);
  * they are all back.  h: column-major host matrix (pinned for the overlap to happen), leading dimension ldh >= m;
  * packed = 0: the whole m x n matrix, of which only this rank's tile columns are read and written; packed = 1: this
  * rank's tile columns only, consecutive in increasing order.  kernel_ms (optional): the kernel's run time, which here
- * includes waiting for its input. */
+ * includes waiting for its input.  As above, a barrier belongs between factor_host and the next reset_host. */
 int    b200qr_dist_reset_host(b200qr_dist_t d);
 int    b200qr_dist_factor_host(b200qr_dist_t d, float *h, long long ldh, int packed, float *kernel_ms);
 int    b200qr_dist_connect_local(b200qr_dist_t *all, int world);

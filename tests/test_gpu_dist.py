@@ -158,6 +158,26 @@ def test_tensor_core_engine_on_two_real_gpus(cuda):
     assert "host identical: True" in r.stdout, r.stdout[-2000:]      # b200qr_dist_factor_host, copies overlapped
 
 
+def test_simt_engine_on_two_real_gpus(cuda):
+    """The SIMT engine's multi-GPU form (sweeps read the panel owner's reflector tiles, tau and progress words over
+    NVLink inside the kernel) on two real GPUs: bit-identical to one GPU, also through the overlapped host path."""
+    import os
+    import subprocess
+    import sys
+    torch = cuda
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, QRB200_WATCHDOG_MS="30000", QRB200_TC="0")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29535",
+                        os.path.join(root, "tools", "dist_tc3_check.py"), "4096"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "single-GPU variant 2" in r.stdout and "identical: True" in r.stdout, r.stdout[-2000:]
+    assert "host identical: True" in r.stdout, r.stdout[-2000:]
+
+
 def test_tsqr_split_over_two_real_gpus(cuda):
     """configs[3] on two GPUs (TsqrDist: local streaming reduction, NCCL all-gather of the R factors, redundant top
     reduction): same R on both ranks, R^T R = A^T A.  Needs two visible GPUs (skipped on a one-GPU box)."""
