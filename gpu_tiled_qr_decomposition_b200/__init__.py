@@ -28,7 +28,7 @@ EXPORTS = (
     "b200qr_sched_rank_tickets_skew", "b200qr_sched_sweep_order_lag",
     "b200qr_dist_create", "b200qr_dist_destroy", "b200qr_dist_handle_bytes", "b200qr_dist_export",
     "b200qr_dist_connect", "b200qr_dist_matrix", "b200qr_dist_tau_device", "b200qr_dist_block",
-    "b200qr_dist_owner", "b200qr_dist_grid", "b200qr_dist_variant", "b200qr_dist_read_trace", "b200qr_dist_tile_tasks", "b200qr_dist_reset", "b200qr_dist_factor", "b200qr_dist_reset_host", "b200qr_dist_factor_host",
+    "b200qr_dist_owner", "b200qr_dist_grid", "b200qr_dist_variant", "b200qr_dist_read_trace", "b200qr_dist_tile_tasks", "b200qr_dist_reset", "b200qr_dist_factor", "b200qr_dist_reset_host", "b200qr_dist_factor_host", "b200qr_plan_stall_info", "b200qr_plan_stall_notes", "b200qr_dist_stall_info",
     "b200qr_dist_connect_local", "b200qr_dist_factor_group",
     "b200qr_batched_workspace_floats", "b200qr_batched_factor", "b200qr_batched_last_cuda_error",
     "b200qr_tsqr_create", "b200qr_tsqr_create_streaming", "b200qr_tsqr_create_tiles", "b200qr_tsqr_leaves", "b200qr_tsqr_stream_block_rows", "b200qr_tsqr_create_rstack", "b200qr_tsqr_destroy", "b200qr_tsqr_levels", "b200qr_tsqr_factor",
@@ -168,6 +168,9 @@ def lib():
         L.b200qr_dist_tile_tasks.restype = C.c_long
         L.b200qr_dist_factor.argtypes = [vp, vp]
         L.b200qr_dist_reset_host.argtypes = [vp]
+        L.b200qr_plan_stall_info.argtypes = [vp, vp]
+        L.b200qr_plan_stall_notes.argtypes = [vp, vp, C.c_int]
+        L.b200qr_dist_stall_info.argtypes = [vp, vp]
         L.b200qr_dist_factor_host.argtypes = [vp, vp, C.c_longlong, C.c_int, C.POINTER(C.c_float)]
         L.b200qr_dist_connect_local.argtypes = [C.POINTER(vp), C.c_int]
         L.b200qr_dist_factor_group.argtypes = [C.POINTER(vp), C.c_int, vp]
@@ -245,6 +248,19 @@ class Plan:
         o = Opts()
         o.grid_ctas, o.trace, o.engine = int(grid_ctas), int(trace), int(engine)
         check(lib().b200qr_plan_create(C.byref(self._h), m, n, C.byref(o)), "b200qr_plan_create")
+
+    def stall_info(self):
+        """After a stall (launch failure): (valid, block, warp, tag, arg) of the first wait that gave up."""
+        out = (C.c_uint * 5)()
+        check(lib().b200qr_plan_stall_info(self._h, out), "b200qr_plan_stall_info")
+        return tuple(out)
+
+    def stall_notes(self):
+        """{(block, warp): (tag, arg)} of every warp that gave up waiting before the kernel trapped."""
+        cap = 16 * 256
+        out = (C.c_uint * (2 * cap))()
+        n = lib().b200qr_plan_stall_notes(self._h, out, cap)
+        return {(s // 16, s % 16): (out[2 * s], out[2 * s + 1] & 0x7fffffff) for s in range(max(n, 0)) if out[2 * s + 1]}
 
     @property
     def grid(self):

@@ -77,6 +77,7 @@ struct Params {
     int *trace;               // optional: 2 ints (start, finish) per tile task
     const long long *trace_off;  // K entries: first trace slot of step k
     unsigned long long watchdog_ns;
+    unsigned *stall;          // pinned host memory (mapped): where a wait that tripped the watchdog was stuck
 };
 
 template <int NC>
@@ -137,19 +138,36 @@ __device__ __forceinline__ unsigned long long gtimer()
 // on the kernel's run time: every waiting loop owns a Spin, whose clock starts at its first check (16384 polls in), so a
 // long factorisation under throttled clocks, a sanitizer or a profiler is not killed as long as it keeps moving.
 struct Spin { unsigned n = 0; unsigned long long since = 0; };
+constexpr int STALL_BLOCKS = 256;                       // blocks with a slot per warp in the watchdog's note area
+constexpr int STALL_WORDS = 8 + 2 * 16 * STALL_BLOCKS;
 struct Watch {
     unsigned long long t0, limit;
+    unsigned *stall;
     // the slow path lives out of line: the waiting loops of the tensor-core engine's chain warps are the critical path
-    // of the whole factorisation and sensitive to every instruction compiled into them
-    __device__ __noinline__ void slow(Spin &s) const
+    // of the whole factorisation and sensitive to every instruction compiled into them.
+    // Before it traps, the first warp to give up leaves a note in pinned HOST memory -- the context is gone after a trap,
+    // host memory is not: {1, block, warp, tag, parity / target} with tag = the shared-memory address of the mbarrier it
+    // waited on, or 0xF0000000 + what for a progress-word wait (b200qr_plan_stall_info).
+    __device__ __noinline__ void slow(Spin &s, unsigned tag, unsigned arg) const
     {
         const unsigned long long now = gtimer();
         if (s.since == 0) s.since = now;
-        else if (now - s.since > limit) __trap();
+        else if (now - s.since > limit) {
+            // every warp that gives up leaves its own note {tag, arg} at stall[8 + 2 (16 block + warp)] and keeps waiting
+            // for another second before it traps, so that the host sees ALL the waits that were stuck, not only the first
+            if (stall) {
+                volatile unsigned *n = stall + 8 + 2 * (16 * blockIdx.x + (threadIdx.x >> 5));
+                if (blockIdx.x < STALL_BLOCKS) { n[0] = tag; n[1] = arg | 0x80000000u; }
+                n = stall;
+                n[1] = blockIdx.x; n[2] = threadIdx.x >> 5; n[3] = tag; n[4] = arg; n[0] = 1u;
+                __threadfence_system();
+            }
+            if (now - s.since > limit + 1000000000ull) __trap();
+        }
     }
-    __device__ __forceinline__ void check(Spin &s) const
+    __device__ __forceinline__ void check(Spin &s, unsigned tag = 0xF0000000u, unsigned arg = 0) const
     {
-        if (((++s.n) & 0x3fffu) == 0) slow(s);
+        if (((++s.n) & 0x3fffu) == 0) slow(s, tag, arg);
     }
 };
 
@@ -158,13 +176,13 @@ struct Watch {
 __device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity, const Watch &w)
 {
     Spin spins;
-    while (!mbar_try_wait(bar, parity)) w.check(spins);
+    while (!mbar_try_wait(bar, parity)) w.check(spins, smem_u32(bar), parity);
 }
 // Spin (whole warp, one coalesced L2 load per iteration) until *p >= target, then acquire.
 __device__ __forceinline__ void wait_flag(const int *p, int target, const Watch &w)
 {
     Spin spins;
-    while (ld_relaxed(p) < target) { __nanosleep(32); w.check(spins); }
+    while (ld_relaxed(p) < target) { __nanosleep(32); w.check(spins, 0xF0000001u, (unsigned)target); }
     __threadfence();
 }
 // acquire / release fences at the scope the run needs (system scope once peers read our memory)
@@ -515,7 +533,7 @@ tiledqr_persistent(const __grid_constant__ KernelArgs KA)
     uint64_t *full = bars, *computed = bars + C::NS, *empty = bars + 2 * C::NS, *pfull = bars + 3 * C::NS;
     int *s_task = reinterpret_cast<int *>(bars + 3 * C::NS + 2 * NPW_SPLIT);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const Watch wd{gtimer(), P.watchdog_ns};
+    const Watch wd{gtimer(), P.watchdog_ns, P.stall};
     const bool split = P.npanel_ctas > 0;
     const bool panel_cta = !split || bid < P.npanel_ctas;
     const bool sweep_cta = !split || bid >= P.npanel_ctas;
@@ -744,6 +762,7 @@ struct b200qr_plan_s {
     float *d_W = nullptr;                    // variant 5: m x (6*K*32) workspace, six blocks (V, T, V^T: hi and lo), tile (i,k) like A
     std::vector<long long> trace_off;
     unsigned long long watchdog_ns;
+    unsigned *h_stall = nullptr, *d_stall = nullptr;   // mapped pinned host memory: the watchdog's note (Watch::slow)
 };
 
 typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -773,8 +792,16 @@ static int make_tile_map(CUtensorMap *map, float *dA, int m, int n, int ldm, boo
     cuuint64_t dims[2] = {(cuuint64_t)m, (cuuint64_t)n};
     cuuint64_t strides[1] = {(cuuint64_t)ldm * sizeof(float)};
     cuuint32_t box[2] = {TB, (cuuint32_t)box_cols}, estr[2] = {1, 1};
+    // L2 promotion: a tile's column is one 128-byte line; QRB200_L2PROMO = 256 makes a load bring in the neighbouring
+    // line too (the same column of the tile row above / below, which the sweep asks for one row later)
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    if (const char *e = getenv("QRB200_L2PROMO")) {
+        const int v = atoi(e);
+        promo = v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+              : v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    }
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dA, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, promo,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? B200QR_OK : B200QR_ECUDA;
 }
@@ -834,6 +861,11 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
     pl->trace = opts ? opts->trace : 0;
     const char *wd = getenv("QRB200_WATCHDOG_MS");
     pl->watchdog_ns = (unsigned long long)(wd ? atol(wd) : 60000) * 1000000ull;
+    // the watchdog's note lives in mapped pinned host memory: it survives the trap that follows it
+    if (cudaHostAlloc((void **)&pl->h_stall, STALL_WORDS * sizeof(unsigned), cudaHostAllocMapped) == cudaSuccess) {
+        memset(pl->h_stall, 0, STALL_WORDS * sizeof(unsigned));
+        if (cudaHostGetDevicePointer((void **)&pl->d_stall, pl->h_stall, 0) != cudaSuccess) pl->d_stall = nullptr;
+    } else { (void)cudaGetLastError(); pl->h_stall = nullptr; }
 
     const int p = pl->p, q = pl->q, K = pl->K;
     pl->trace_off.resize(K);
@@ -981,6 +1013,8 @@ static void plan_free(b200qr_plan_s *pl)
     cudaFree(pl->d_prog); cudaFree(pl->d_ctr); cudaFree(pl->d_sweep_tab); cudaFree(pl->d_panel_tab); cudaFree(pl->d_tauc);
     cudaFree(pl->d_trace); cudaFree(pl->d_trace_off);
     cudaFree(pl->d_W);
+    if (pl->h_stall) cudaFreeHost(pl->h_stall);
+    pl->h_stall = pl->d_stall = nullptr;
 }
 
 // Fills one rank slot of the kernel arguments (dA/ldm = this rank's matrix).
@@ -996,6 +1030,7 @@ static int fill_rank_ctx(RankCtx *rc, b200qr_plan_s *pl, float *dA, int ldm)
     P.trace = (pl->trace && pl->trace != 3) ? pl->d_trace : nullptr; P.trace_off = pl->d_trace_off; P.trace_mode = pl->trace;
     if (getenv("QRB200_ONE_ENGINE")) P.trace_mode = 7;
     P.watchdog_ns = pl->watchdog_ns;
+    P.stall = pl->d_stall;
     for (int r = 0; r < pl->world; ++r) { P.peer_prog[r] = pl->peer_prog[r]; P.peer_tauc[r] = pl->peer_tauc[r]; P.prog_w[r] = pl->peer_prog[r]; }
     int rc_ = make_tile_map(&rc->mapA, dA, pl->m, pl->n, ldm, true);
     for (int r = 0; r < pl->world && rc_ == B200QR_OK; ++r) {
@@ -1024,6 +1059,7 @@ static int reset_progress(b200qr_plan_s *pl, cudaStream_t stream, int fill = 0)
 {
     CK(cudaMemsetAsync(pl->d_prog, fill, sizeof(int) * (size_t)pl->p * pl->q, stream));
     CK(cudaMemsetAsync(pl->d_ctr, 0, sizeof(int) * CTR_INTS, stream));
+    if (pl->h_stall) memset(pl->h_stall, 0, STALL_WORDS * sizeof(unsigned));
     if (pl->trace && pl->trace != 3) CK(cudaMemsetAsync(pl->d_trace, 0xff, sizeof(int) * 2 * (size_t)pl->tile_tasks, stream));
     return B200QR_OK;
 }
@@ -1053,6 +1089,24 @@ int b200qr_plan_destroy(b200qr_plan_t pl)
     return B200QR_OK;
 }
 
+// After B200QR_ESTALL (or a launch failure seen by the caller's own synchronize): where the first wait that gave up was
+// stuck.  out5 = {valid, block, warp, tag, arg}: tag = shared-memory address of the mbarrier (arg = the parity waited
+// for), or 0xF0000000 + n for a progress-word wait (arg = the value waited for).  Readable although the context is dead.
+int b200qr_plan_stall_info(b200qr_plan_t pl, unsigned *out5)
+{
+    if (!pl || !out5) return B200QR_EINVAL;
+    for (int i = 0; i < 5; ++i) out5[i] = pl->h_stall ? ((volatile unsigned *)pl->h_stall)[i] : 0u;
+    return B200QR_OK;
+}
+// every stuck warp's note: out[2 (16 block + warp)] = tag, [.. + 1] = arg | 0x80000000 (0 = that warp left none); returns the
+// number of (block, warp) slots written to out (cap = slots the caller has room for)
+int b200qr_plan_stall_notes(b200qr_plan_t pl, unsigned *out, int cap)
+{
+    if (!pl || !out || cap < 0) return B200QR_EINVAL;
+    const int n = cap < 16 * STALL_BLOCKS ? cap : 16 * STALL_BLOCKS;
+    for (int i = 0; i < 2 * n; ++i) out[i] = pl->h_stall ? ((volatile unsigned *)pl->h_stall)[8 + i] : 0u;
+    return n;
+}
 int b200qr_plan_grid(b200qr_plan_t pl) { return pl ? pl->grid : B200QR_EINVAL; }
 int b200qr_plan_variant(b200qr_plan_t pl) { return pl ? pl->nc : B200QR_EINVAL; }
 int b200qr_plan_debug_counters(b200qr_plan_t pl, unsigned long long *out, int n)
@@ -1153,6 +1207,7 @@ float *b200qr_dist_matrix(b200qr_dist_t d) { return d ? d->dA : nullptr; }
 int b200qr_dist_block(b200qr_dist_t d) { return d ? d->plan.G : B200QR_EINVAL; }
 int b200qr_dist_owner(b200qr_dist_t d, int tile_col) { return d ? (tile_col / d->plan.G) % d->plan.world : B200QR_EINVAL; }
 int b200qr_dist_grid(b200qr_dist_t d) { return d ? d->plan.grid : B200QR_EINVAL; }
+int b200qr_dist_stall_info(b200qr_dist_t d, unsigned *out5) { return d ? b200qr_plan_stall_info(&d->plan, out5) : B200QR_EINVAL; }
 int b200qr_dist_variant(b200qr_dist_t d) { return d ? d->plan.nc : B200QR_EINVAL; }
 const float *b200qr_dist_tau_device(b200qr_dist_t d) { return d ? d->plan.d_tauc : nullptr; }
 

@@ -86,6 +86,14 @@ int         b200qr_measure_fp32_peak(double *gflops, int iters);
 int  b200qr_plan_create(b200qr_plan_t *plan, int m, int n, const b200qr_opts *opts);
 int  b200qr_plan_destroy(b200qr_plan_t plan);
 int  b200qr_plan_grid(b200qr_plan_t plan);               /* CTAs the kernel launches with */
+/* After B200QR_ESTALL (or a launch failure the caller's own synchronize reported): where the first wait that gave up was
+ * stuck.  out5 = {valid, block, warp, tag, arg}; tag = shared-memory address of the mbarrier it waited on (arg = parity),
+ * or 0xF0000000 + n for a progress-word wait (arg = the value waited for).  The note lives in pinned host memory, so it
+ * can be read although the CUDA context is gone. */
+int  b200qr_plan_stall_info(b200qr_plan_t plan, unsigned *out5);
+/* Every warp that gave up leaves a note and waits one more second before it traps, so all the stuck waits are on record:
+ * out[2 s] = tag, out[2 s + 1] = arg | 0x80000000 for slot s = 16 * block + warp (0 = none); returns the slots copied. */
+int  b200qr_plan_stall_notes(b200qr_plan_t plan, unsigned *out, int cap);
 int  b200qr_plan_debug_counters(b200qr_plan_t plan, unsigned long long *out, int n);   /* opts.trace == 3: phase timers of the tensor-core engine */
 int  b200qr_plan_variant(b200qr_plan_t plan);            /* 1, 2: FP32 SIMT sweeps (1 / 2 matrix columns per thread); 5: tcgen05 sweeps */
 long b200qr_plan_tile_tasks(b200qr_plan_t plan);         /* sum_k (p-k)(q-k)  (gpucalc.cu:1546-1559) */
@@ -136,6 +144,7 @@ const float *b200qr_dist_tau_device(b200qr_dist_t d);        /* compact tau [(k*
 int    b200qr_dist_block(b200qr_dist_t d);                   /* tile columns per distribution block */
 int    b200qr_dist_owner(b200qr_dist_t d, int tile_col);     /* rank that owns a tile column */
 int    b200qr_dist_grid(b200qr_dist_t d);
+int    b200qr_dist_stall_info(b200qr_dist_t d, unsigned *out5);   /* like b200qr_plan_stall_info */
 int  b200qr_dist_variant(b200qr_dist_t d);             /* kernel variant of this rank's plan (2: SIMT sweeps, 5: tensor-core engine) */
 int    b200qr_dist_read_trace(b200qr_dist_t d, int *out6, long cap);   /* opts.trace; tasks of other ranks read -1 */
 long   b200qr_dist_tile_tasks(b200qr_dist_t d);

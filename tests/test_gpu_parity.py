@@ -302,3 +302,16 @@ def test_reference_selftest_against_the_b200_library(cuda, po, tiles):
     n = tiles * 32
     tasks = sum((tiles - k) * (tiles - k) for k in range(tiles))
     assert "(%d,%d)" % (n, n) in r.stdout and "%d tasks" % tasks in r.stdout     # the legacy prints (gpucalc.cu:1557)
+
+
+def test_a_stalled_factorisation_traps_and_says_where(cuda):
+    """A wait that makes no progress for QRB200_WATCHDOG_MS traps the kernel (no hung GPU) and leaves a note in pinned host
+    memory that b200qr_*_stall_info can still read: tools/stall_demo.py launches one rank of a two-rank world alone."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, QRB200_WATCHDOG_MS="1500")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "stall_demo.py")], capture_output=True, text=True,
+                       timeout=120, env=env)
+    assert "launch failed" in r.stdout and "stall info rc 0 valid 1" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
