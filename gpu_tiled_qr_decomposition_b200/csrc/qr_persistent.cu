@@ -792,13 +792,14 @@ static int make_tile_map(CUtensorMap *map, float *dA, int m, int n, int ldm, boo
     cuuint64_t dims[2] = {(cuuint64_t)m, (cuuint64_t)n};
     cuuint64_t strides[1] = {(cuuint64_t)ldm * sizeof(float)};
     cuuint32_t box[2] = {TB, (cuuint32_t)box_cols}, estr[2] = {1, 1};
-    // L2 promotion: a tile's column is one 128-byte line; QRB200_L2PROMO = 256 makes a load bring in the neighbouring
-    // line too (the same column of the tile row above / below, which the sweep asks for one row later)
-    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    // L2 promotion 256 B: a tile's column is one 128-byte line, and a load brings in the neighbouring line too -- the same
+    // column of the tile row above / below, which the sweep asks for one row later (16384^2 132.4 -> 131.4 ms, 32768^2
+    // 1003.6 -> 993.2 ms; 64 B = 128 B; nothing for the SIMT engine).  QRB200_L2PROMO = 128 / 64 / 0 for A/B runs.
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     if (const char *e = getenv("QRB200_L2PROMO")) {
         const int v = atoi(e);
-        promo = v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-              : v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+        promo = v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+              : v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     }
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dA, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, promo,
