@@ -1,15 +1,10 @@
 #!/bin/bash
-# A/B: L2 promotion of the tensor maps (QRB200_L2PROMO = 128 default / 256 / 64 / 0).
+# Round-end validation session: the GPU suite, smoke(), the default bench line and the reference arm.
+# Run on a B200 box:  gpurun --timeout 3600 -- 'bash tools/gpu_session.sh'
 mkdir -p gpurun_out
-T=gpurun_out/s50
-for rep in 1 2; do
-  for pr in 128 256 64; do
-    QRB200_L2PROMO=$pr timeout 300 python tools/tc3_time.py 16384 3 2>&1 | grep -v Warn | sed "s/^/promo $pr /" >> ${T}_promo.log
-  done
-done
-for pr in 128 256; do
-  QRB200_L2PROMO=$pr timeout 300 python tools/tc3_time.py 32768 3 2>&1 | grep -v Warn | sed "s/^/promo $pr /" >> ${T}_promo.log
-  QRB200_L2PROMO=$pr QRB200_TC=0 timeout 300 python tools/tc3_time.py 8192 0 2>&1 | grep -v Warn | sed "s/^/promo $pr /" >> ${T}_promo.log
-  QRB200_L2PROMO=$pr QRB200_TC=0 timeout 300 python tools/tc3_time.py 12288 0 2>&1 | grep -v Warn | sed "s/^/promo $pr /" >> ${T}_promo.log
-done
-cat ${T}_promo.log
+T=gpurun_out/final
+timeout 2400 python -m pytest tests -m gpu -q -x > ${T}_tests.log 2>&1; echo "tests rc=$?" >> ${T}_tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > ${T}_smoke.log 2>&1
+timeout 900 python bench.py --steps 5 --warmup 3 > ${T}_bench.log 2>&1
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > ${T}_ref.log 2>&1
+tail -3 ${T}_tests.log; tail -2 ${T}_smoke.log; tail -c 600 ${T}_bench.log
