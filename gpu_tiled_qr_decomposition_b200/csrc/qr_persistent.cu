@@ -911,8 +911,11 @@ static int plan_build(b200qr_plan_s *pl, int m, int n, int rank, int world, int 
         double ptiles = 0, stiles = 0;
         for (int k = 0; k < K; ++k) { ptiles += p - k; stiles += (double)(p - k) * (q - k - 1); }
         int want = 2;
+        // (a rank runs the panels of ITS tile columns only: 1 / world of them.  Until late round 2 the model charged
+        //  every rank with all panels, which at 8 ranks set aside 30 of the 148 CTAs for panels where 4 are enough:
+        //  32768^2 on 8 GPUs 185.2 ms with the old count, 166.8 ms with 4 panel CTAs -- tools/dist_scan.py)
         for (; want < grid / 4; ++want) {
-            const double t_panel = ptiles * 7.2 / (NPW_SPLIT * want);
+            const double t_panel = ptiles / world * 7.2 / (NPW_SPLIT * want);
             const double t_sweep = stiles * 0.54 / ((double)world * (grid - want));
             if (t_panel <= 0.4 * t_sweep) break;
         }
